@@ -1,0 +1,222 @@
+"""Kernel-level parity (GPU): every C-ABI entry point against a plain torch fp32 restatement of the same
+op (floating point) or the numpy oracle (index kernels, bit-exact)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import swin3d_oracle as O  # noqa: E402
+from tests.helpers import rel_err  # noqa: E402
+
+BF16_TOL = 1e-2   # bf16 operands + bf16 output rounding (2^-9 per element), fp32 accumulation
+
+
+def _ops():
+    import vsn_b200  # noqa: F401
+    from vsn_b200 import ops
+    return ops
+
+
+def _bf(t):
+    return t.to(torch.bfloat16)
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).cuda()
+
+
+# ----------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K", [(256, 96, 64), (1000, 288, 96), (4096, 384, 96), (777, 96, 384),
+                                   (252, 768, 3072), (130, 1152, 384), (8, 64, 4096), (300, 2304, 768)])
+def test_gemm_forward_bias(M, N, K):
+    ops = _ops()
+    x, w, b = _bf(_rand(M, K, seed=1)), _bf(_rand(N, K, seed=2, scale=K ** -0.5)), _rand(N, seed=3)
+    y = ops.linear_fwd(x, w, b)
+    ref = x.float() @ w.float().t() + b
+    assert rel_err(y.float(), ref) < BF16_TOL
+    y32 = ops.linear_fwd(x, w, b, out_dtype=torch.float32)
+    assert rel_err(y32, ref) < 1e-5
+
+
+def test_gemm_epilogues():
+    ops = _ops()
+    M, N, K, rpg = 600, 384, 96, 200
+    x, w, b = _bf(_rand(M, K, seed=1)), _bf(_rand(N, K, seed=2, scale=K ** -0.5)), _rand(N, seed=3)
+    aux = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    y = ops.linear_fwd(x, w, b, gelu_aux=aux)
+    pre = x.float() @ w.float().t() + b
+    assert rel_err(aux.float(), pre) < BF16_TOL
+    assert rel_err(y.float(), torch.nn.functional.gelu(aux.float())) < BF16_TOL
+    # residual + per-sample scale, fp32 out
+    resid, scale = _rand(M, N, seed=4), torch.tensor([1.0, 0.0, 1.25], device="cuda")
+    y2 = ops.linear_fwd(x, w, b, out_dtype=torch.float32, resid=resid, row_scale=scale, rows_per_group=rpg)
+    ref = resid + scale.repeat_interleave(rpg)[:, None] * pre
+    assert rel_err(y2, ref) < 1e-5
+    # dgrad with fused GELU'
+    dy = _bf(_rand(M, K, seed=5))          # pretend gradient wrt an [M,K] output of a K<-N layer
+    w2 = _bf(_rand(K, N, seed=6, scale=N ** -0.5))   # layer weight [out=K, in=N]
+    dx = ops.linear_dgrad(dy, w2, gelu_aux=aux)
+    a = aux.float().requires_grad_(True)
+    torch.nn.functional.gelu(a).backward(dy.float() @ w2.float())
+    assert rel_err(dx.float(), a.grad) < BF16_TOL
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 96, 96), (3000, 288, 96), (1000, 96, 384), (700, 384, 96),
+                                   (5000, 192, 768), (64, 96, 64), (100, 1536, 384)])
+def test_gemm_dgrad_wgrad(M, N, K):
+    ops = _ops()
+    dy, x, w = _bf(_rand(M, N, seed=1)), _bf(_rand(M, K, seed=2)), _bf(_rand(N, K, seed=3, scale=K ** -0.5))
+    dx = ops.linear_dgrad(dy, w)
+    assert rel_err(dx.float(), dy.float() @ w.float()) < BF16_TOL
+    dw = torch.zeros(N, K, device="cuda")
+    ops.linear_wgrad(dy, x, dw)
+    ref = dy.float().t() @ x.float()
+    assert rel_err(dw, ref) < 1e-4
+    ops.linear_wgrad(dy, x, dw)           # accumulates
+    assert rel_err(dw, 2 * ref) < 1e-4
+
+
+# ----------------------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("rows,C", [(1000, 96), (333, 768), (50, 3072), (17, 4096), (4000, 192)])
+def test_layernorm(rows, C):
+    ops = _ops()
+    x, g, b = _rand(rows, C, seed=1) * 2 + 0.5, 1 + 0.1 * _rand(C, seed=2), 0.1 * _rand(C, seed=3)
+    y, mean, rstd = ops.layernorm_fwd(x, g, b, out_dtype=torch.float32)
+    xr = x.clone().requires_grad_(True)
+    gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (C,), gr, br, 1e-5)
+    assert rel_err(y, ref) < 1e-5
+    yb, _, _ = ops.layernorm_fwd(x, g, b)
+    assert rel_err(yb.float(), ref) < BF16_TOL
+    dy = _rand(rows, C, seed=4)
+    ref.backward(dy)
+    rg = _rand(rows, C, seed=5)
+    dx, dxb = ops.layernorm_bwd(dy, x, mean, rstd, g, resid_grad=rg, want_bf16=True)
+    assert rel_err(dx, xr.grad + rg) < 1e-5
+    assert rel_err(dxb.float(), xr.grad + rg) < BF16_TOL
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    ops.ln_param_grad(dy, x, mean, rstd, dg, db)
+    assert rel_err(dg, gr.grad) < 1e-4 and rel_err(db, br.grad) < 1e-4
+    cs = torch.zeros(C, device="cuda")
+    ops.colsum(_bf(dy), cs)
+    assert rel_err(cs, _bf(dy).float().sum(0)) < 1e-4
+
+
+# ----------------------------------------------------------------------------- attention
+def _ref_window_attention(qkv, table, B, grid, window, shift, shifted, heads, hd):
+    """fp32 torch restatement on the gathered windows (oracle index tables)."""
+    T, _ = qkv.shape
+    C = heads * hd
+    tok = torch.from_numpy(O.window_tokens(grid, window)).cuda()
+    nW, N = tok.shape
+    src = torch.from_numpy(O.shifted_source(grid, shift)).cuda()[tok] if shifted else tok
+    x = qkv.reshape(B, -1, 3, heads, hd)[:, src.reshape(-1)].reshape(B * nW, N, 3, heads, hd)
+    q, k, v = (x[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    s = (q @ k.transpose(-1, -2)) * hd ** -0.5
+    rpi = torch.from_numpy(O.relative_position_index(window)).cuda()
+    s = s + table[rpi.reshape(-1)].reshape(N, N, heads).permute(2, 0, 1)[None]
+    if shifted:
+        m = torch.from_numpy(O.shift_mask(grid, window, shift)).cuda()
+        s = (s.reshape(B, nW, heads, N, N) + m[None, :, None]).reshape(B * nW, heads, N, N)
+    o = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B, nW * N, C)
+    out = torch.zeros(B, grid[0] * grid[1] * grid[2], C, device="cuda", dtype=o.dtype)
+    out[:, src.reshape(-1)] = o
+    return out.reshape(T, C)
+
+
+@pytest.mark.parametrize("grid,heads,shifted", [((12, 14, 12), 2, False), ((12, 14, 12), 2, True),
+                                                ((6, 7, 6), 3, True), ((18, 21, 12), 1, True)])
+def test_window_attention_fwd_bwd(grid, heads, shifted):
+    ops = _ops()
+    B, window, shift, hd = 2, (6, 7, 6), (3, 3, 3), 32
+    C = heads * hd
+    T = B * grid[0] * grid[1] * grid[2]
+    qkv = _bf(_rand(T, 3 * C, seed=1))
+    table = 0.5 * _rand(11 * 13 * 11, heads, seed=2)
+    geom = ops.WindowGeom(B, grid, window, shift if shifted else (0, 0, 0), shifted)
+    out, lse = ops.attn_fwd(qkv, heads, hd, S=geom.S, N=geom.N, scale=hd ** -0.5, geom=geom, table=table)
+    q32 = qkv.float().requires_grad_(True)
+    t32 = table.clone().requires_grad_(True)
+    ref = _ref_window_attention(q32, t32, B, grid, window, shift, shifted, heads, hd)
+    assert rel_err(out.float(), ref) < BF16_TOL
+    dout = _bf(_rand(T, C, seed=3))
+    ref.backward(dout.float())
+    dtable = torch.zeros_like(table)
+    dqkv = ops.attn_bwd(qkv, out, dout, lse, heads, hd, S=geom.S, N=geom.N, scale=hd ** -0.5, geom=geom, table=table,
+                        dtable=dtable)
+    assert rel_err(dqkv.float(), q32.grad) < 2e-2
+    assert rel_err(dtable, t32.grad) < 2e-2
+
+
+@pytest.mark.parametrize("N,heads", [(13, 2), (81, 2), (811, 6)])
+def test_dense_attention_fwd_bwd(N, heads):
+    ops = _ops()
+    B, hd = 2, 64
+    C = heads * hd
+    qkv = _bf(_rand(B * N, 3 * C, seed=1))
+    out, lse = ops.attn_fwd(qkv, heads, hd, S=B, N=N, scale=hd ** -0.5)
+    q32 = qkv.float().requires_grad_(True)
+    x = q32.reshape(B, N, 3, heads, hd)
+    q, k, v = (x[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    ref = (torch.softmax((q @ k.transpose(-1, -2)) * hd ** -0.5, -1) @ v).permute(0, 2, 1, 3).reshape(B * N, C)
+    assert rel_err(out.float(), ref) < BF16_TOL
+    dout = _bf(_rand(B * N, C, seed=3))
+    ref.backward(dout.float())
+    dqkv = ops.attn_bwd(qkv, out, dout, lse, heads, hd, S=B, N=N, scale=hd ** -0.5)
+    assert rel_err(dqkv.float(), q32.grad) < 2e-2
+
+
+# ----------------------------------------------------------------------------- layout kernels (bit-exact)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_patch_gather_bit_exact(dtype):
+    ops = _ops()
+    B, D, H, W, p = 2, 10, 13, 7, (4, 4, 4)
+    vol = _rand(B, 1, D, H, W, seed=1).to(dtype)
+    rows = ops.patch_gather(vol, p, out_dtype=torch.float32)
+    v = torch.nn.functional.pad(vol.float(), (0, (-W) % 4, 0, (-H) % 4, 0, (-D) % 4))
+    gd, gh, gw = v.shape[2] // 4, v.shape[3] // 4, v.shape[4] // 4
+    ref = v.reshape(B, gd, 4, gh, 4, gw, 4).permute(0, 1, 3, 5, 2, 4, 6).reshape(B * gd * gh * gw, 64)
+    assert torch.equal(rows, ref)
+
+
+def test_grid_copy_and_merge_gather_bit_exact():
+    ops = _ops()
+    B, C = 2, 32
+    real, padded = (7, 8, 5), (12, 14, 6)
+    x = _rand(B * real[0] * real[1] * real[2], C, seed=1)
+    xp = ops.grid_copy(x, real, padded, B, C)
+    ref = torch.nn.functional.pad(x.reshape(B, *real, C), (0, 0, 0, padded[2] - real[2], 0, padded[1] - real[1], 0,
+                                                             padded[0] - real[0]))
+    assert torch.equal(xp.reshape(B, *padded, C), ref)
+    back = ops.grid_copy(xp, padded, real, B, C)
+    assert torch.equal(back, x)
+    g = ops.merge_gather(xp, padded, real, B, C)
+    t = torch.nn.functional.pad(x.reshape(B, *real, C), (0, 0, 0, real[2] % 2, 0, real[1] % 2, 0, real[0] % 2))
+    parts = [t[:, a::2, b::2, c::2] for (a, b, c) in
+             ((0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 0), (1, 0, 1), (0, 1, 1), (1, 1, 1))]
+    refg = torch.cat(parts, -1).reshape(-1, 8 * C)
+    assert torch.equal(g, refg)
+    # scatter is the exact transpose of gather
+    dx = ops.merge_scatter(g, padded, real, B, C)
+    assert torch.equal(dx.reshape(B, *padded, C)[:, :real[0], :real[1], :real[2]], x.reshape(B, *real, C))
+    assert float(dx.abs().sum()) == float(x.abs().sum())
+
+
+def test_head_and_token_mean():
+    ops = _ops()
+    B, T, F_, K = 3, 150, 768, 5
+    x, W, b = _rand(B * T, F_, seed=1), _rand(K, F_, seed=2, scale=0.05), _rand(K, seed=3)
+    pooled = ops.token_mean(x, B, T, F_)
+    assert rel_err(pooled, x.reshape(B, T, F_).mean(1)) < 1e-6
+    logits = ops.head_fwd(pooled, W, b)
+    assert rel_err(logits, pooled @ W.t() + b) < 1e-5
+    dl = _rand(B, K, seed=4)
+    dW, db = torch.zeros_like(W), torch.zeros_like(b)
+    dfeat = ops.head_bwd(dl, pooled, W, dW, db)
+    assert rel_err(dfeat, dl @ W) < 1e-5 and rel_err(dW, dl.t() @ pooled) < 1e-5 and rel_err(db, dl.sum(0)) < 1e-5
+    dx = ops.token_mean_bwd(dfeat, B, T, F_)
+    assert rel_err(dx.reshape(B, T, F_), (dfeat / T)[:, None].expand(B, T, F_)) < 1e-6

@@ -1,0 +1,83 @@
+"""ctypes binding of the C ABI declared in include/vsn_b200.h.
+
+There is no fallback: if the shared library is missing, or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvsn_b200.so")
+
+_p, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+
+# name -> argtypes (restype is int unless noted)
+SIGNATURES = {
+    "vsn_version": [],
+    "vsn_check_device": [],
+    "vsn_gemm_bf16": [_p, _ll, _i, _p, _ll, _i, _i, _i, _i, _p, _ll, _i, _p, _i, _p, _ll, _p, _ll, _p, _i, _f, _i, _p],
+    "vsn_layernorm_fwd": [_p, _ll, _p, _p, _p, _ll, _i, _p, _p, _ll, _i, _f, _p],
+    "vsn_layernorm_bwd": [_p, _ll, _i, _p, _ll, _p, _p, _p, _p, _ll, _p, _ll, _p, _ll, _p, _i, _ll, _i, _p],
+    "vsn_colreduce": [_p, _ll, _i, _p, _ll, _p, _p, _p, _p, _ll, _i, _p],
+    "vsn_attn_fwd": [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _f, _p],
+    "vsn_attn_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _f, _p],
+    "vsn_patch_gather": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "vsn_grid_copy": [_p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p],
+    "vsn_merge_gather": [_p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _p],
+    "vsn_cast_rows_bf16": [_p, _p, _p, _i, _ll, _i, _p],
+    "vsn_cast_bf16": [_p, _p, _ll, _p],
+    "vsn_token_mean": [_p, _p, _i, _i, _i, _i, _p],
+    "vsn_head_fwd": [_p, _p, _p, _p, _i, _i, _i, _p],
+    "vsn_head_bwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "vsn_vit_assemble": [_p, _p, _p, _p, _i, _i, _i, _p],
+    "vsn_vit_assemble_bwd": [_p, _p, _p, _i, _i, _i, _p],
+    "vsn_mt_chunk_elems": [],
+    "vsn_mt_sqnorm": [_p, _p, _p, _p, _p, _i, _p, _i, _p],
+    "vsn_sam_scale": [_p, _i, _f, _p, _p, _p],
+    "vsn_mt_sam_perturb": [_p, _p, _p, _p, _p, _p, _i, _p, _p, _i, _p],
+    "vsn_mt_copy": [_p, _p, _p, _p, _p, _i, _p],
+    "vsn_mt_ema": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _f, _f, _f, _p],
+}
+
+_lib = None
+_device_checked = False
+
+
+def load() -> C.CDLL:
+    """Load libvsn_b200.so (building is `__graft_entry__.build()`'s job, not ours)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python __graft_entry__.py build` "
+                "(vsn_b200 has no fallback path)")
+        lib = C.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the ABI and the binding disagree
+            fn.argtypes = args
+            fn.restype = C.c_int
+        lib.vsn_last_error.argtypes = []
+        lib.vsn_last_error.restype = C.c_char_p
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return load().vsn_last_error().decode("utf-8", "replace")
+
+
+def check_device() -> None:
+    global _device_checked
+    if not _device_checked:
+        lib = load()
+        if lib.vsn_check_device() != 0:
+            raise RuntimeError("vsn_b200: " + last_error())
+        _device_checked = True
+
+
+def call(name: str, *args) -> None:
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed (code {rc}): {last_error()}")

@@ -1,0 +1,40 @@
+// C-ABI plumbing shared by every entry point: error string, version, device gate.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void vsn_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int vsn_num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+extern "C" const char* vsn_last_error() { return g_err; }
+
+extern "C" int vsn_version() { return 100; }
+
+// 0 when the current device can run this library (compute capability 10.x); the Python side
+// refuses to continue otherwise -- there is no fallback path.
+extern "C" int vsn_check_device() {
+  int dev = 0;
+  VSN_CUDA(cudaGetDevice(&dev));
+  int major = 0, minor = 0;
+  VSN_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  VSN_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  VSN_CHECK(major == 10, "vsn_b200 kernels are built for sm_100a only; device %d is sm_%d%d", dev, major, minor);
+  return 0;
+}

@@ -1,0 +1,327 @@
+// Data-movement kernels around the GEMMs: patch gather (im2col of non-overlapping patches),
+// stage pad/crop, patch-merging gather/scatter, row casts, token mean and the tiny classifier head.
+// All are index math + coalesced 16-byte accesses; none of them re-reads data.
+#include "common.cuh"
+
+namespace {
+
+template <typename T>
+__device__ __forceinline__ float ld_as_float(const T* p);
+template <>
+__device__ __forceinline__ float ld_as_float<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float ld_as_float<__half>(const __half* p) { return __half2float(*p); }
+template <>
+__device__ __forceinline__ float ld_as_float<bf16>(const bf16* p) { return __bfloat162float(*p); }
+
+__device__ __forceinline__ void st_from_float(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st_from_float(bf16* p, float v) { *p = __float2bfloat16(v); }
+
+// out[(b,d,h,w), (i,j,k)] = vol[b, d*pd+i, h*ph+j, w*pw+k]  (zero beyond D,H,W).
+// PatchEmbed3D's pad + Conv3d(k=s=patch) operand (models/swin_transformer_3d.py:532-539) and the ViT
+// Rearrange 'b c (d p1)(h p2)(w p3) -> b (d h w)(p1 p2 p3 c)' with c=1 (models/vit_3d.py:365-370).
+// One thread per (token, i, j): it copies the pw contiguous voxels of one patch row.
+template <typename InT, typename OutT>
+__global__ void patch_gather_kernel(const InT* __restrict__ vol, OutT* __restrict__ out, int B, int D, int H, int W,
+                                    int gd, int gh, int gw, int pd, int ph, int pw) {
+  const long long total = static_cast<long long>(B) * gd * gh * gw * pd * ph;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    // order (b, d, h, i, j, w): consecutive threads walk w, so global reads of one (i,j) row are contiguous
+    long long t = idx;
+    const int w = static_cast<int>(t % gw); t /= gw;
+    const int j = static_cast<int>(t % ph); t /= ph;
+    const int i = static_cast<int>(t % pd); t /= pd;
+    const int h = static_cast<int>(t % gh); t /= gh;
+    const int d = static_cast<int>(t % gd); t /= gd;
+    const int b = static_cast<int>(t);
+    const int zd = d * pd + i, zh = h * ph + j;
+    const long long token = ((static_cast<long long>(b) * gd + d) * gh + h) * gw + w;
+    OutT* o = out + token * (pd * ph * pw) + (i * ph + j) * pw;
+    const bool ok = zd < D && zh < H;
+    const InT* src = vol + ((static_cast<long long>(b) * D + zd) * H + zh) * W + static_cast<long long>(w) * pw;
+    for (int k = 0; k < pw; ++k) {
+      const float v = (ok && w * pw + k < W) ? ld_as_float<InT>(src + k) : 0.f;
+      st_from_float(o + k, v);
+    }
+  }
+}
+
+// Copy the overlapping box of two channels-last grids and zero-fill the rest of dst.
+// pad (models/swin_transformer_3d.py:457-461) when dst is larger, crop (:508) when smaller.
+__global__ void grid_copy_kernel(const float* __restrict__ src, int sD, int sH, int sW, float* __restrict__ dst,
+                                 int dD, int dH, int dW, int B, int C4) {
+  const long long total = static_cast<long long>(B) * dD * dH * dW * C4;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    long long t = idx;
+    const int c = static_cast<int>(t % C4); t /= C4;
+    const int w = static_cast<int>(t % dW); t /= dW;
+    const int h = static_cast<int>(t % dH); t /= dH;
+    const int d = static_cast<int>(t % dD); t /= dD;
+    const int b = static_cast<int>(t);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (d < sD && h < sH && w < sW)
+      v = reinterpret_cast<const float4*>(src)[(((static_cast<long long>(b) * sD + d) * sH + h) * sW + w) * C4 + c];
+    reinterpret_cast<float4*>(dst)[idx] = v;
+  }
+}
+
+// PatchMerging gather (models/swin_transformer_3d.py:553-568): out[(b,d,h,w), q*C + c] = x[b, 2d+od, 2h+oh, 2w+ow, c]
+// with q enumerating (od,oh,ow) = (0,0,0),(1,0,0),(0,1,0),(0,0,1),(1,1,0),(1,0,1),(0,1,1),(1,1,1); positions
+// outside the REAL grid (rD,rH,rW) read as zero (crop + odd pad); x lives on the padded stage grid (pD,pH,pW).
+// scatter=true runs the same index map backwards (gradient): x[...] = out[...], untouched positions keep
+// their (pre-zeroed) value.
+template <bool SCATTER>
+__global__ void merge_gather_kernel(float* __restrict__ x, int pD, int pH, int pW, int rD, int rH, int rW,
+                                    float* __restrict__ out, int oD, int oH, int oW, int B, int C4) {
+  const long long total = static_cast<long long>(B) * oD * oH * oW * 8 * C4;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    long long t = idx;
+    const int c = static_cast<int>(t % C4); t /= C4;
+    const int q = static_cast<int>(t % 8); t /= 8;
+    const int w = static_cast<int>(t % oW); t /= oW;
+    const int h = static_cast<int>(t % oH); t /= oH;
+    const int d = static_cast<int>(t % oD); t /= oD;
+    const int b = static_cast<int>(t);
+    // q -> (od, oh, ow) in the reference's concatenation order
+    const int od = (0xB2 >> q) & 1;  // q: 0 1 2 3 4 5 6 7 -> 0 1 0 0 1 1 0 1
+    const int oh = (0xD4 >> q) & 1;  //                    -> 0 0 1 0 1 0 1 1
+    const int ow = (0xE8 >> q) & 1;  //                    -> 0 0 0 1 0 1 1 1
+    const int sd = 2 * d + od, sh = 2 * h + oh, sw = 2 * w + ow;
+    const bool ok = sd < rD && sh < rH && sw < rW;
+    float4* xp = reinterpret_cast<float4*>(x) + (((static_cast<long long>(b) * pD + sd) * pH + sh) * pW + sw) * C4 + c;
+    float4* op = reinterpret_cast<float4*>(out) + idx;
+    if (SCATTER) {
+      if (ok) *xp = *op;
+    } else {
+      *op = ok ? *xp : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+// dst_bf16[r, c] = src_f32[r, c] * row_scale[r / rows_per_group]
+__global__ void cast_rows_kernel(const float* __restrict__ src, bf16* __restrict__ dst, const float* __restrict__ scale,
+                                 int rows_per_group, long long rows, int C4) {
+  const long long total = rows * C4;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const float4 v = reinterpret_cast<const float4*>(src)[idx];
+    const float s = scale ? scale[(idx / C4) / rows_per_group] : 1.f;
+    uint2 u;
+    u.x = pack_bf16(v.x * s, v.y * s);
+    u.y = pack_bf16(v.z * s, v.w * s);
+    reinterpret_cast<uint2*>(dst)[idx] = u;
+  }
+}
+
+// fp32 -> bf16 over a flat range (weights)
+__global__ void cast_flat_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = __float2bfloat16(src[i]);
+}
+
+// out[b, c] = mean_t x[b, t, c]  (AdaptiveAvgPool3d(1), models/swin_transformer_3d.py:696) and its gradient
+__global__ void token_mean_kernel(const float* __restrict__ x, float* __restrict__ out, int T, int C) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float* p = x + static_cast<long long>(b) * T * C + c;
+  float s = 0.f;
+  for (int t = 0; t < T; ++t) s += p[static_cast<long long>(t) * C];
+  out[static_cast<long long>(b) * C + c] = s / T;
+}
+__global__ void token_mean_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dx, int T, int C) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float v = dout[static_cast<long long>(b) * C + c] / T;
+  float* p = dx + static_cast<long long>(b) * T * C + c;
+  for (int t = 0; t < T; ++t) p[static_cast<long long>(t) * C] = v;
+}
+
+// logits[b,k] = sum_f feat[b,f] * W[k,f] + bias[k]   (head Linear, fp32; K is a handful of classes)
+__global__ void head_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ W,
+                                const float* __restrict__ bias, float* __restrict__ logits, int B, int K, int F) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B * K) return;
+  const int b = warp / K, k = warp % K;
+  float s = 0.f;
+  for (int f = lane; f < F; f += 32) s += feat[static_cast<long long>(b) * F + f] * W[static_cast<long long>(k) * F + f];
+  s = warp_sum(s);
+  if (lane == 0) logits[warp] = s + (bias ? bias[k] : 0.f);
+}
+// dfeat[b,f] = sum_k dl[b,k] W[k,f];  dW[k,f] += sum_b dl[b,k] feat[b,f];  db[k] += sum_b dl[b,k]
+__global__ void head_bwd_kernel(const float* __restrict__ dl, const float* __restrict__ feat,
+                                const float* __restrict__ W, float* __restrict__ dfeat, float* __restrict__ dW,
+                                float* __restrict__ db, int B, int K, int F) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < F) {
+    for (int b = 0; b < B; ++b) {
+      float s = 0.f;
+      for (int k = 0; k < K; ++k) s += dl[b * K + k] * W[static_cast<long long>(k) * F + f];
+      dfeat[static_cast<long long>(b) * F + f] = s;
+    }
+    for (int k = 0; k < K; ++k) {
+      float s = 0.f;
+      for (int b = 0; b < B; ++b) s += dl[b * K + k] * feat[static_cast<long long>(b) * F + f];
+      dW[static_cast<long long>(k) * F + f] += s;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < K && db != nullptr) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += dl[b * K + threadIdx.x];
+    db[threadIdx.x] += s;
+  }
+}
+
+// ViT token assembly (models/vit_3d.py:447-449): x[b,0,:] = cls + pos[0]; x[b,1+t,:] = emb[b,t,:] + pos[1+t]
+__global__ void vit_assemble_kernel(const float* __restrict__ emb, const float* __restrict__ cls,
+                                    const float* __restrict__ pos, float* __restrict__ x, int B, int T, int C4) {
+  const long long total = static_cast<long long>(B) * (T + 1) * C4;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    long long t = idx;
+    const int c = static_cast<int>(t % C4); t /= C4;
+    const int tok = static_cast<int>(t % (T + 1)); t /= (T + 1);
+    const int b = static_cast<int>(t);
+    float4 v = tok == 0 ? reinterpret_cast<const float4*>(cls)[c]
+                        : reinterpret_cast<const float4*>(emb)[(static_cast<long long>(b) * T + tok - 1) * C4 + c];
+    const float4 p = reinterpret_cast<const float4*>(pos)[static_cast<long long>(tok) * C4 + c];
+    reinterpret_cast<float4*>(x)[idx] = make_float4(v.x + p.x, v.y + p.y, v.z + p.z, v.w + p.w);
+  }
+}
+// gradient of the above: dpos[tok] += sum_b dx[b,tok]; dcls += sum_b dx[b,0]  (demb is dx[:,1:] read in place)
+__global__ void vit_assemble_bwd_kernel(const float* __restrict__ dx, float* __restrict__ dcls,
+                                        float* __restrict__ dpos, int B, int T, int C) {
+  const long long total = static_cast<long long>(T + 1) * C;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += dx[static_cast<long long>(b) * total + idx];
+    dpos[idx] += s;
+    if (idx < C) dcls[idx] += s;
+  }
+}
+
+inline unsigned grid_for(long long total, int block) {
+  long long g = ceil_div_ll(total, block);
+  const long long cap = static_cast<long long>(vsn_num_sms()) * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<unsigned>(g);
+}
+
+}  // namespace
+
+// in_dtype: 0 fp32, 1 fp16, 2 bf16.  out_bf16: 1 -> bf16 rows (GEMM operand), 0 -> fp32 rows (feeds LayerNorm).
+extern "C" int vsn_patch_gather(const void* vol, int in_dtype, void* out, int out_bf16, int B, int D, int H, int W,
+                                int pd, int ph, int pw, void* stream) {
+  const int gd = ceil_div(D, pd), gh = ceil_div(H, ph), gw = ceil_div(W, pw);
+  const long long total = static_cast<long long>(B) * gd * gh * gw * pd * ph;
+  if (total == 0) return 0;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned grid = grid_for(total, 256);
+#define VSN_PG(InT, OutT)                                                                                          \
+  patch_gather_kernel<InT, OutT><<<grid, 256, 0, s>>>(reinterpret_cast<const InT*>(vol), reinterpret_cast<OutT*>(out), \
+                                                     B, D, H, W, gd, gh, gw, pd, ph, pw)
+  if (in_dtype == 0 && out_bf16) VSN_PG(float, bf16);
+  else if (in_dtype == 0) VSN_PG(float, float);
+  else if (in_dtype == 1 && out_bf16) VSN_PG(__half, bf16);
+  else if (in_dtype == 1) VSN_PG(__half, float);
+  else if (in_dtype == 2 && out_bf16) VSN_PG(bf16, bf16);
+  else if (in_dtype == 2) VSN_PG(bf16, float);
+  else { vsn_set_error("vsn_patch_gather: bad in_dtype %d", in_dtype); return 1; }
+#undef VSN_PG
+  VSN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vsn_grid_copy(const float* src, int sD, int sH, int sW, float* dst, int dD, int dH, int dW, int B,
+                             int C, void* stream) {
+  VSN_CHECK(C % 4 == 0, "vsn_grid_copy: C must be a multiple of 4");
+  const long long total = static_cast<long long>(B) * dD * dH * dW * (C / 4);
+  if (total == 0) return 0;
+  grid_copy_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, sD, sH, sW, dst, dD,
+                                                                                            dH, dW, B, C / 4);
+  VSN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vsn_merge_gather(float* x, int pD, int pH, int pW, int rD, int rH, int rW, float* out, int B, int C,
+                                int scatter, void* stream) {
+  VSN_CHECK(C % 4 == 0, "vsn_merge_gather: C must be a multiple of 4");
+  const int oD = (rD + 1) / 2, oH = (rH + 1) / 2, oW = (rW + 1) / 2;
+  const long long total = static_cast<long long>(B) * oD * oH * oW * 8 * (C / 4);
+  if (total == 0) return 0;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (scatter)
+    merge_gather_kernel<true><<<grid_for(total, 256), 256, 0, s>>>(x, pD, pH, pW, rD, rH, rW, out, oD, oH, oW, B, C / 4);
+  else
+    merge_gather_kernel<false><<<grid_for(total, 256), 256, 0, s>>>(x, pD, pH, pW, rD, rH, rW, out, oD, oH, oW, B, C / 4);
+  VSN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vsn_cast_rows_bf16(const float* src, void* dst, const float* row_scale, int rows_per_group,
+                                  long long rows, int C, void* stream) {
+  VSN_CHECK(C % 4 == 0, "vsn_cast_rows_bf16: C must be a multiple of 4");
+  const long long total = rows * (C / 4);
+  if (total == 0) return 0;
+  cast_rows_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src, reinterpret_cast<bf16*>(dst), row_scale, rows_per_group > 0 ? rows_per_group : 1, rows, C / 4);
+  VSN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vsn_cast_bf16(const float* src, void* dst, long long n, void* stream) {
+  if (n == 0) return 0;
+  cast_flat_kernel<<<grid_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, reinterpret_cast<bf16*>(dst), n);
+  VSN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vsn_token_mean(const float* x, float* out, int B, int T, int C, int backward, void* stream) {
+  if (B == 0 || T == 0 || C == 0) return 0;
+  dim3 grid(ceil_div(C, 128), B);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (backward) token_mean_bwd_kernel<<<grid, 128, 0, s>>>(x, out, T, C);   // x = d(out) [B,C], out = dx [B,T,C]
+  else token_mean_kernel<<<grid, 128, 0, s>>>(x, out, T, C);
+  VSN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vsn_head_fwd(const float* feat, const float* W, const float* bias, float* logits, int B, int K, int F,
+                            void* stream) {
+  if (B * K == 0) return 0;
+  head_fwd_kernel<<<ceil_div(B * K * 32, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(feat, W, bias, logits, B, K, F);
+  VSN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vsn_head_bwd(const float* dlogits, const float* feat, const float* W, float* dfeat, float* dW,
+                            float* db, int B, int K, int F, void* stream) {
+  VSN_CHECK(K <= 128, "vsn_head_bwd: at most 128 classes (got %d)", K);
+  if (B * K == 0) return 0;
+  head_bwd_kernel<<<ceil_div(F, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dlogits, feat, W, dfeat, dW, db, B, K, F);
+  VSN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vsn_vit_assemble(const float* emb, const float* cls, const float* pos, float* x, int B, int T, int C,
+                                void* stream) {
+  VSN_CHECK(C % 4 == 0, "vsn_vit_assemble: C must be a multiple of 4");
+  const long long total = static_cast<long long>(B) * (T + 1) * (C / 4);
+  vit_assemble_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(emb, cls, pos, x, B, T, C / 4);
+  VSN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vsn_vit_assemble_bwd(const float* dx, float* dcls, float* dpos, int B, int T, int C, void* stream) {
+  const long long total = static_cast<long long>(T + 1) * C;
+  vit_assemble_bwd_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dx, dcls, dpos, B, T, C);
+  VSN_LAUNCH_CHECK();
+  return 0;
+}

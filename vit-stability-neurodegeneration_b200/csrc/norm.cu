@@ -1,0 +1,281 @@
+// LayerNorm forward / backward and column reductions (HBM-bound kernels).
+// Replaces nn.LayerNorm on the path: norm1/norm2 (models/swin_transformer_3d.py:236,255,330,373),
+// PatchEmbed3D.norm (:541), PatchMerging.norm (:570), backbone.norm (:693), and the ViT norms
+// (models/vit_3d.py:69,98,371,373,401).  eps = 1e-5, biased variance, statistics in fp32.
+#include "common.cuh"
+
+namespace {
+
+constexpr int LN_WARPS = 8;
+
+template <typename T>
+__device__ __forceinline__ float to_f(T v);
+template <>
+__device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+
+__device__ __forceinline__ void store_out(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store_out(bf16* p, float v) { *p = __float2bfloat16(v); }
+
+// One warp per row.  Rows up to 1024 wide are held in registers (one HBM read); wider rows are
+// re-read from L1/L2 for the second and third sweep.
+template <typename OutT>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const float* __restrict__ x, long long ldx,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, OutT* __restrict__ y,
+                                                               long long ldy, float* __restrict__ mean_out,
+                                                               float* __restrict__ rstd_out, long long rows, int C,
+                                                               float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * ldx;
+  OutT* yr = y + row * ldy;
+  const int nvec = C >> 2;  // C is a multiple of 4
+  if (nvec <= 256) {
+    float4 v[8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = lane + i * 32;
+      if (j < nvec) {
+        v[i] = *reinterpret_cast<const float4*>(xr + 4 * j);
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+    }
+    const float mu = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = lane + i * 32;
+      if (j < nvec) {
+        const float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / C + eps);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = lane + i * 32;
+      if (j < nvec) {
+        const float4 g = *reinterpret_cast<const float4*>(gamma + 4 * j);
+        const float4 b = *reinterpret_cast<const float4*>(beta + 4 * j);
+        const float o0 = (v[i].x - mu) * rstd * g.x + b.x, o1 = (v[i].y - mu) * rstd * g.y + b.y;
+        const float o2 = (v[i].z - mu) * rstd * g.z + b.z, o3 = (v[i].w - mu) * rstd * g.w + b.w;
+        if constexpr (sizeof(OutT) == 2) {
+          uint2 u;
+          u.x = pack_bf16(o0, o1);
+          u.y = pack_bf16(o2, o3);
+          *reinterpret_cast<uint2*>(yr + 4 * j) = u;
+        } else {
+          *reinterpret_cast<float4*>(yr + 4 * j) = make_float4(o0, o1, o2, o3);
+        }
+      }
+    }
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mu;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+  } else {
+    float s = 0.f;
+    for (int j = lane; j < nvec; j += 32) {
+      const float4 t = *reinterpret_cast<const float4*>(xr + 4 * j);
+      s += (t.x + t.y) + (t.z + t.w);
+    }
+    const float mu = warp_sum(s) / C;
+    float q = 0.f;
+    for (int j = lane; j < nvec; j += 32) {
+      const float4 t = *reinterpret_cast<const float4*>(xr + 4 * j);
+      const float a = t.x - mu, b = t.y - mu, c = t.z - mu, d = t.w - mu;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / C + eps);
+    for (int j = lane; j < nvec; j += 32) {
+      const float4 t = *reinterpret_cast<const float4*>(xr + 4 * j);
+      const float4 g = *reinterpret_cast<const float4*>(gamma + 4 * j);
+      const float4 b = *reinterpret_cast<const float4*>(beta + 4 * j);
+      const float o0 = (t.x - mu) * rstd * g.x + b.x, o1 = (t.y - mu) * rstd * g.y + b.y;
+      const float o2 = (t.z - mu) * rstd * g.z + b.z, o3 = (t.w - mu) * rstd * g.w + b.w;
+      if constexpr (sizeof(OutT) == 2) {
+        uint2 u;
+        u.x = pack_bf16(o0, o1);
+        u.y = pack_bf16(o2, o3);
+        *reinterpret_cast<uint2*>(yr + 4 * j) = u;
+      } else {
+        *reinterpret_cast<float4*>(yr + 4 * j) = make_float4(o0, o1, o2, o3);
+      }
+    }
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mu;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+  }
+}
+
+// dx = rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat)) [+ resid_grad]; optional bf16 copy of
+// dx scaled per row group (the DropPath factor of the branch that consumes it next).
+template <typename DyT>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const DyT* __restrict__ dy, long long lddy,
+                                                               const float* __restrict__ x, long long ldx,
+                                                               const float* __restrict__ mean,
+                                                               const float* __restrict__ rstd,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ resid_grad, long long ldr,
+                                                               float* __restrict__ dx, long long lddx,
+                                                               bf16* __restrict__ dx_bf16, long long ldb,
+                                                               const float* __restrict__ row_scale,
+                                                               int rows_per_group, long long rows, int C) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const DyT* dyr = dy + row * lddy;
+  const float* xr = x + row * ldx;
+  const float mu = mean[row], rs = rstd[row];
+  float s1 = 0.f, s2 = 0.f;
+  for (int j = lane * 4; j < C; j += 128) {
+    const float4 xv = *reinterpret_cast<const float4*>(xr + j);
+    const float4 g = *reinterpret_cast<const float4*>(gamma + j);
+    float d0, d1, d2, d3;
+    if constexpr (sizeof(DyT) == 2) {
+      const uint2 u = *reinterpret_cast<const uint2*>(dyr + j);
+      const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+      d0 = a.x; d1 = a.y; d2 = b.x; d3 = b.y;
+    } else {
+      const float4 t = *reinterpret_cast<const float4*>(dyr + j);
+      d0 = t.x; d1 = t.y; d2 = t.z; d3 = t.w;
+    }
+    d0 *= g.x; d1 *= g.y; d2 *= g.z; d3 *= g.w;
+    s1 += (d0 + d1) + (d2 + d3);
+    s2 += (d0 * (xv.x - mu) + d1 * (xv.y - mu)) + (d2 * (xv.z - mu) + d3 * (xv.w - mu));
+  }
+  s1 = warp_sum(s1) / C;
+  s2 = warp_sum(s2) * rs / C;  // mean(dy*g*xhat)
+  float scale = 1.f;
+  if (dx_bf16 != nullptr && row_scale != nullptr) scale = row_scale[row / rows_per_group];
+  for (int j = lane * 4; j < C; j += 128) {
+    const float4 xv = *reinterpret_cast<const float4*>(xr + j);
+    const float4 g = *reinterpret_cast<const float4*>(gamma + j);
+    float d0, d1, d2, d3;
+    if constexpr (sizeof(DyT) == 2) {
+      const uint2 u = *reinterpret_cast<const uint2*>(dyr + j);
+      const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+      d0 = a.x; d1 = a.y; d2 = b.x; d3 = b.y;
+    } else {
+      const float4 t = *reinterpret_cast<const float4*>(dyr + j);
+      d0 = t.x; d1 = t.y; d2 = t.z; d3 = t.w;
+    }
+    float o0 = rs * (d0 * g.x - s1 - (xv.x - mu) * rs * s2);
+    float o1 = rs * (d1 * g.y - s1 - (xv.y - mu) * rs * s2);
+    float o2 = rs * (d2 * g.z - s1 - (xv.z - mu) * rs * s2);
+    float o3 = rs * (d3 * g.w - s1 - (xv.w - mu) * rs * s2);
+    if (resid_grad != nullptr) {
+      const float4 r = *reinterpret_cast<const float4*>(resid_grad + row * ldr + j);
+      o0 += r.x; o1 += r.y; o2 += r.z; o3 += r.w;
+    }
+    if (dx != nullptr) *reinterpret_cast<float4*>(dx + row * lddx + j) = make_float4(o0, o1, o2, o3);
+    if (dx_bf16 != nullptr) {
+      uint2 u;
+      u.x = pack_bf16(o0 * scale, o1 * scale);
+      u.y = pack_bf16(o2 * scale, o3 * scale);
+      *reinterpret_cast<uint2*>(dx_bf16 + row * ldb + j) = u;
+    }
+  }
+}
+
+// Column reductions over rows: dbeta[c] += sum_r dy[r,c]; dgamma[c] += sum_r dy[r,c]*xhat[r,c].
+// With x == nullptr it is a plain column sum (bias gradients of the Linear layers).
+constexpr int CR_TX = 32, CR_TY = 8, CR_ROWS = 256;
+template <typename DyT>
+__global__ void __launch_bounds__(CR_TX * CR_TY) colreduce_kernel(const DyT* __restrict__ dy, long long lddy,
+                                                                  const float* __restrict__ x, long long ldx,
+                                                                  const float* __restrict__ mean,
+                                                                  const float* __restrict__ rstd,
+                                                                  float* __restrict__ dgamma,
+                                                                  float* __restrict__ dbeta, long long rows, int C) {
+  __shared__ float sg[CR_TY][CR_TX + 1], sb[CR_TY][CR_TX + 1];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = blockIdx.x * CR_TX + tx;
+  const long long r0 = static_cast<long long>(blockIdx.y) * CR_ROWS;
+  const long long r1 = r0 + CR_ROWS < rows ? r0 + CR_ROWS : rows;
+  float ag = 0.f, ab = 0.f;
+  if (c < C) {
+    for (long long r = r0 + ty; r < r1; r += CR_TY) {
+      const float d = to_f<DyT>(dy[r * lddy + c]);
+      ab += d;
+      if (x != nullptr) ag += d * (x[r * ldx + c] - mean[r]) * rstd[r];
+    }
+  }
+  sg[ty][tx] = ag;
+  sb[ty][tx] = ab;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+#pragma unroll
+    for (int i = 1; i < CR_TY; ++i) {
+      ag += sg[i][tx];
+      ab += sb[i][tx];
+    }
+    if (dbeta != nullptr) atomicAdd(dbeta + c, ab);
+    if (dgamma != nullptr && x != nullptr) atomicAdd(dgamma + c, ag);
+  }
+}
+
+}  // namespace
+
+extern "C" int vsn_layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, void* y,
+                                 long long ldy, int y_bf16, float* mean, float* rstd, long long rows, int C,
+                                 float eps, void* stream) {
+  VSN_CHECK(C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "vsn_layernorm_fwd: C/ld must be multiples of 4 (C=%d)", C);
+  if (rows == 0) return 0;
+  const unsigned grid = static_cast<unsigned>(ceil_div_ll(rows, LN_WARPS));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (y_bf16)
+    ln_fwd_kernel<bf16><<<grid, LN_WARPS * 32, 0, s>>>(x, ldx, gamma, beta, reinterpret_cast<bf16*>(y), ldy, mean,
+                                                         rstd, rows, C, eps);
+  else
+    ln_fwd_kernel<float><<<grid, LN_WARPS * 32, 0, s>>>(x, ldx, gamma, beta, reinterpret_cast<float*>(y), ldy, mean,
+                                                          rstd, rows, C, eps);
+  VSN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vsn_layernorm_bwd(const void* dy, long long lddy, int dy_bf16, const float* x, long long ldx,
+                                 const float* mean, const float* rstd, const float* gamma, const float* resid_grad,
+                                 long long ldr, float* dx, long long lddx, void* dx_bf16, long long ldb,
+                                 const float* row_scale, int rows_per_group, long long rows, int C, void* stream) {
+  VSN_CHECK(C % 4 == 0, "vsn_layernorm_bwd: C must be a multiple of 4 (C=%d)", C);
+  if (rows == 0) return 0;
+  const unsigned grid = static_cast<unsigned>(ceil_div_ll(rows, LN_WARPS));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int rpg = rows_per_group > 0 ? rows_per_group : 1;
+  if (dy_bf16)
+    ln_bwd_kernel<bf16><<<grid, LN_WARPS * 32, 0, s>>>(reinterpret_cast<const bf16*>(dy), lddy, x, ldx, mean, rstd,
+                                                         gamma, resid_grad, ldr, dx, lddx,
+                                                         reinterpret_cast<bf16*>(dx_bf16), ldb, row_scale, rpg, rows, C);
+  else
+    ln_bwd_kernel<float><<<grid, LN_WARPS * 32, 0, s>>>(reinterpret_cast<const float*>(dy), lddy, x, ldx, mean,
+                                                          rstd, gamma, resid_grad, ldr, dx, lddx,
+                                                          reinterpret_cast<bf16*>(dx_bf16), ldb, row_scale, rpg, rows,
+                                                          C);
+  VSN_LAUNCH_CHECK();
+  return 0;
+}
+
+// dgamma/dbeta (x != null) or a plain column sum into dbeta (x == null).  Accumulates (+=).
+extern "C" int vsn_colreduce(const void* dy, long long lddy, int dy_bf16, const float* x, long long ldx,
+                             const float* mean, const float* rstd, float* dgamma, float* dbeta, long long rows, int C,
+                             void* stream) {
+  if (rows == 0 || C == 0) return 0;
+  dim3 grid(ceil_div(C, CR_TX), static_cast<unsigned>(ceil_div_ll(rows, CR_ROWS)));
+  VSN_CHECK(grid.y <= 65535, "vsn_colreduce: too many rows (%lld)", rows);
+  dim3 block(CR_TX, CR_TY);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (dy_bf16)
+    colreduce_kernel<bf16><<<grid, block, 0, s>>>(reinterpret_cast<const bf16*>(dy), lddy, x, ldx, mean, rstd, dgamma,
+                                                    dbeta, rows, C);
+  else
+    colreduce_kernel<float><<<grid, block, 0, s>>>(reinterpret_cast<const float*>(dy), lddy, x, ldx, mean, rstd,
+                                                     dgamma, dbeta, rows, C);
+  VSN_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,201 @@
+// HBM-bound multi-tensor kernels for the optimiser side of the path:
+//   SAM  (regularization/sam.py:38-155): per-tensor gradient norms, global norm, perturb (+save), restore
+//   EMA  (utils/ema.py:72-108): on-device ring of the last 3 snapshots + weighted average
+// One launch walks every parameter tensor through a chunk table (tensor id, element offset), so the
+// reference's per-parameter Python loops and host syncs (isnan/isinf -> bool) disappear.
+#include "common.cuh"
+
+namespace {
+
+constexpr int MT_CHUNK = 16384;   // elements per block
+constexpr int MT_THREADS = 256;
+
+struct MTTable {
+  const long long* sizes;         // [n_tensors]
+  const int* chunk_tensor;        // [n_chunks]
+  const long long* chunk_off;     // [n_chunks]
+};
+
+__device__ __forceinline__ bool chunk_span(const MTTable& t, int& tensor, long long& off, long long& n) {
+  tensor = t.chunk_tensor[blockIdx.x];
+  off = t.chunk_off[blockIdx.x];
+  const long long left = t.sizes[tensor] - off;
+  n = left < MT_CHUNK ? left : MT_CHUNK;
+  return n > 0;
+}
+
+// sq[t] += sum (w * g)^2 over the chunk, w = |p| if adaptive else 1
+__global__ void __launch_bounds__(MT_THREADS) mt_sqnorm_kernel(const long long* g_ptrs, const long long* p_ptrs,
+                                                               MTTable tab, float* sq, int adaptive) {
+  int tensor; long long off, n;
+  if (!chunk_span(tab, tensor, off, n)) return;
+  const float* g = reinterpret_cast<const float*>(g_ptrs[tensor]) + off;
+  const float* p = adaptive ? reinterpret_cast<const float*>(p_ptrs[tensor]) + off : nullptr;
+  float acc = 0.f;
+  const bool vec = ((reinterpret_cast<uintptr_t>(g) | (p ? reinterpret_cast<uintptr_t>(p) : 0)) & 15) == 0;
+  if (vec) {
+    const long long n4 = n >> 2;
+    for (long long i = threadIdx.x; i < n4; i += MT_THREADS) {
+      float4 v = reinterpret_cast<const float4*>(g)[i];
+      if (adaptive) {
+        const float4 w = reinterpret_cast<const float4*>(p)[i];
+        v.x *= fabsf(w.x); v.y *= fabsf(w.y); v.z *= fabsf(w.z); v.w *= fabsf(w.w);
+      }
+      acc += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    }
+    for (long long i = (n4 << 2) + threadIdx.x; i < n; i += MT_THREADS) {
+      const float v = adaptive ? g[i] * fabsf(p[i]) : g[i];
+      acc += v * v;
+    }
+  } else {
+    for (long long i = threadIdx.x; i < n; i += MT_THREADS) {
+      const float v = adaptive ? g[i] * fabsf(p[i]) : g[i];
+      acc += v * v;
+    }
+  }
+  __shared__ float red[MT_THREADS / 32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < MT_THREADS / 32 ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(sq + tensor, v);
+  }
+}
+
+// Global SAM norm from the per-tensor sums of squares, with the reference's finite-ness rules:
+// tensors whose norm is NaN/Inf are left out (and flagged so the perturbation skips them); an empty or
+// non-finite total becomes 1e-12; a zero total disables the perturbation.
+// out[0] = scale = rho / (norm + 1e-12) (0 when skipped), out[1] = norm.
+__global__ void sam_scale_kernel(const float* sq, int n, float rho, float* out, int* skip_flags) {
+  __shared__ double red[32];
+  __shared__ int cnt[32];
+  double acc = 0.0;
+  int c = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float nrm = sqrtf(sq[i]);
+    const bool ok = isfinite(nrm);
+    skip_flags[i] = ok ? 0 : 1;
+    if (ok) { acc += static_cast<double>(nrm) * nrm; ++c; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = acc; cnt[threadIdx.x >> 5] = c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0; int k = 0;
+    for (int i = 0; i < (blockDim.x + 31) / 32; ++i) { tot += red[i]; k += cnt[i]; }
+    float norm = k == 0 ? 1e-12f : static_cast<float>(sqrt(tot));
+    if (!isfinite(norm)) norm = 1e-12f;
+    out[1] = norm;
+    out[0] = (norm == 0.f) ? 0.f : rho / (norm + 1e-12f);
+  }
+}
+
+// old = p;  p += (p^2 if adaptive else 1) * g * scale   (skipped per tensor flag / when scale == 0)
+__global__ void __launch_bounds__(MT_THREADS) mt_sam_perturb_kernel(const long long* p_ptrs, const long long* g_ptrs,
+                                                                    const long long* old_ptrs, MTTable tab,
+                                                                    const float* scale_dev, const int* skip_flags,
+                                                                    int adaptive) {
+  int tensor; long long off, n;
+  if (!chunk_span(tab, tensor, off, n)) return;
+  float* p = reinterpret_cast<float*>(p_ptrs[tensor]) + off;
+  const float* g = reinterpret_cast<const float*>(g_ptrs[tensor]) + off;
+  float* old = reinterpret_cast<float*>(old_ptrs[tensor]) + off;
+  const float scale = skip_flags[tensor] ? 0.f : scale_dev[0];
+  for (long long i = threadIdx.x; i < n; i += MT_THREADS) {
+    const float w = p[i];
+    old[i] = w;
+    if (scale != 0.f) p[i] = w + (adaptive ? w * w : 1.0f) * g[i] * scale;
+  }
+}
+
+__global__ void __launch_bounds__(MT_THREADS) mt_copy_kernel(const long long* dst_ptrs, const long long* src_ptrs,
+                                                             MTTable tab) {
+  int tensor; long long off, n;
+  if (!chunk_span(tab, tensor, off, n)) return;
+  float* d = reinterpret_cast<float*>(dst_ptrs[tensor]) + off;
+  const float* s = reinterpret_cast<const float*>(src_ptrs[tensor]) + off;
+  for (long long i = threadIdx.x; i < n; i += MT_THREADS) d[i] = s[i];
+}
+
+// slot_new = p;  ema = w0*s0 + w1*s1 + w2*p accumulated oldest -> newest with fma (k = 1..3 live snapshots;
+// the newest is always the current parameters).  Unused older slots are passed as null tables.
+__global__ void __launch_bounds__(MT_THREADS) mt_ema_kernel(const long long* p_ptrs, const long long* new_ptrs,
+                                                            const long long* s0_ptrs, const long long* s1_ptrs,
+                                                            const long long* ema_ptrs, MTTable tab, float w0, float w1,
+                                                            float w2) {
+  int tensor; long long off, n;
+  if (!chunk_span(tab, tensor, off, n)) return;
+  const float* p = reinterpret_cast<const float*>(p_ptrs[tensor]) + off;
+  float* snew = reinterpret_cast<float*>(new_ptrs[tensor]) + off;
+  const float* s0 = s0_ptrs ? reinterpret_cast<const float*>(s0_ptrs[tensor]) + off : nullptr;
+  const float* s1 = s1_ptrs ? reinterpret_cast<const float*>(s1_ptrs[tensor]) + off : nullptr;
+  float* ema = reinterpret_cast<float*>(ema_ptrs[tensor]) + off;
+  for (long long i = threadIdx.x; i < n; i += MT_THREADS) {
+    const float v = p[i];
+    float acc = 0.f;
+    if (s0) acc = fmaf(w0, s0[i], acc);
+    if (s1) acc = fmaf(w1, s1[i], acc);
+    acc = fmaf(w2, v, acc);
+    snew[i] = v;
+    ema[i] = acc;
+  }
+}
+
+}  // namespace
+
+extern "C" int vsn_mt_chunk_elems() { return MT_CHUNK; }
+
+extern "C" int vsn_mt_sqnorm(const long long* g_ptrs, const long long* p_ptrs, const long long* sizes,
+                             const int* chunk_tensor, const long long* chunk_off, int n_chunks, float* sq,
+                             int adaptive, void* stream) {
+  if (n_chunks == 0) return 0;
+  VSN_CHECK(!adaptive || p_ptrs != nullptr, "vsn_mt_sqnorm: adaptive mode needs the parameter pointers");
+  MTTable t{sizes, chunk_tensor, chunk_off};
+  mt_sqnorm_kernel<<<n_chunks, MT_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(g_ptrs, p_ptrs, t, sq, adaptive);
+  VSN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vsn_sam_scale(const float* sq, int n_tensors, float rho, float* out2, int* skip_flags, void* stream) {
+  sam_scale_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(sq, n_tensors, rho, out2, skip_flags);
+  VSN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vsn_mt_sam_perturb(const long long* p_ptrs, const long long* g_ptrs, const long long* old_ptrs,
+                                  const long long* sizes, const int* chunk_tensor, const long long* chunk_off,
+                                  int n_chunks, const float* scale_dev, const int* skip_flags, int adaptive,
+                                  void* stream) {
+  if (n_chunks == 0) return 0;
+  MTTable t{sizes, chunk_tensor, chunk_off};
+  mt_sam_perturb_kernel<<<n_chunks, MT_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p_ptrs, g_ptrs, old_ptrs, t,
+                                                                                             scale_dev, skip_flags, adaptive);
+  VSN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vsn_mt_copy(const long long* dst_ptrs, const long long* src_ptrs, const long long* sizes,
+                           const int* chunk_tensor, const long long* chunk_off, int n_chunks, void* stream) {
+  if (n_chunks == 0) return 0;
+  MTTable t{sizes, chunk_tensor, chunk_off};
+  mt_copy_kernel<<<n_chunks, MT_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dst_ptrs, src_ptrs, t);
+  VSN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vsn_mt_ema(const long long* p_ptrs, const long long* new_ptrs, const long long* s0_ptrs,
+                          const long long* s1_ptrs, const long long* ema_ptrs, const long long* sizes,
+                          const int* chunk_tensor, const long long* chunk_off, int n_chunks, float w0, float w1,
+                          float w2, void* stream) {
+  if (n_chunks == 0) return 0;
+  MTTable t{sizes, chunk_tensor, chunk_off};
+  mt_ema_kernel<<<n_chunks, MT_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p_ptrs, new_ptrs, s0_ptrs, s1_ptrs,
+                                                                                     ema_ptrs, t, w0, w1, w2);
+  VSN_LAUNCH_CHECK();
+  return 0;
+}

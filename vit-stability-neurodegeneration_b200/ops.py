@@ -1,0 +1,268 @@
+"""Tensor-level wrappers over the C ABI: output allocation and argument marshalling only.
+
+Every function enqueues CUDA kernels from libvsn_b200.so on torch's current stream.  Nothing here
+computes with torch ops; torch is the allocator and the stream owner.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+_N_SMS = 148
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("vsn_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    _lib.check_device()
+
+
+# ------------------------------------------------------------------ GEMM family
+def gemm(a, lda, a_mn, b, ldb, b_mn, M, N, K, out, ldo, out_kind, *, bias=None, act=0, aux=None, ldaux=0,
+         resid=None, ldr=0, row_scale=None, rows_per_group=1, alpha=1.0, split_k=1):
+    _require_cuda(a, b, out)
+    _lib.call("vsn_gemm_bf16", _p(a), lda, int(a_mn), _p(b), ldb, int(b_mn), M, N, K, _p(out), ldo, out_kind,
+              _p(bias), act, _p(aux), ldaux, _p(resid), ldr, _p(row_scale), rows_per_group, float(alpha), split_k,
+              _stream())
+
+
+def linear_fwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, out_dtype=BF16,
+               gelu_aux: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None,
+               row_scale: Optional[torch.Tensor] = None, rows_per_group: int = 1,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = x @ w.T (+bias) with the fused epilogues.  x [M,K] bf16, w [N,K] bf16."""
+    M, K = x.shape
+    N = w.shape[0]
+    assert x.dtype == BF16 and w.dtype == BF16 and x.stride(1) == 1 and w.stride(1) == 1
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=out_dtype)
+    gemm(x, x.stride(0), 0, w, w.stride(0), 0, M, N, K, out, out.stride(0), 0 if out.dtype == BF16 else 1,
+         bias=bias, act=1 if gelu_aux is not None else 0, aux=gelu_aux,
+         ldaux=gelu_aux.stride(0) if gelu_aux is not None else 0,
+         resid=resid, ldr=resid.stride(0) if resid is not None else 0, row_scale=row_scale,
+         rows_per_group=rows_per_group)
+    return out
+
+
+def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, *, gelu_aux: Optional[torch.Tensor] = None,
+                 out_dtype=BF16, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dx = dy @ w  (w [N,K] read as stored: MN-major B operand).  Optional fused GELU'(aux) factor."""
+    M, N = dy.shape
+    K = w.shape[1]
+    assert dy.dtype == BF16 and w.dtype == BF16
+    if out is None:
+        out = torch.empty((M, K), device=dy.device, dtype=out_dtype)
+    gemm(dy, dy.stride(0), 0, w, w.stride(0), 1, M, K, N, out, out.stride(0), 0 if out.dtype == BF16 else 1,
+         act=2 if gelu_aux is not None else 0, aux=gelu_aux, ldaux=gelu_aux.stride(0) if gelu_aux is not None else 0)
+    return out
+
+
+def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor) -> None:
+    """dw[N,K] += dy[M,N].T @ x[M,K]  (both operands MN-major, tokens split over CTAs, fp32 atomics)."""
+    M, N = dy.shape
+    K = x.shape[1]
+    assert dy.dtype == BF16 and x.dtype == BF16 and dw.dtype == F32 and dw.is_contiguous()
+    tiles = math.ceil(N / 128) * math.ceil(K / (64 if K <= 64 else 128))
+    nkb = math.ceil(M / 64)
+    split = max(1, min(nkb, (2 * _N_SMS) // max(tiles, 1)))
+    gemm(dy, dy.stride(0), 1, x, x.stride(0), 1, N, K, M, dw, K, 2, split_k=split)
+
+
+# ------------------------------------------------------------------ LayerNorm
+def layernorm_fwd(x: torch.Tensor, gamma, beta, *, out_dtype=BF16, eps: float = 1e-5, want_stats: bool = True):
+    """x fp32 [rows, C] (row stride free).  Returns (y, mean, rstd)."""
+    rows, C = x.shape
+    assert x.dtype == F32 and x.stride(1) == 1
+    _require_cuda(x)
+    y = torch.empty((rows, C), device=x.device, dtype=out_dtype)
+    mean = torch.empty((rows,), device=x.device, dtype=F32) if want_stats else None
+    rstd = torch.empty((rows,), device=x.device, dtype=F32) if want_stats else None
+    _lib.call("vsn_layernorm_fwd", _p(x), x.stride(0), _p(gamma), _p(beta), _p(y), y.stride(0),
+              1 if out_dtype == BF16 else 0, _p(mean), _p(rstd), rows, C, eps, _stream())
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, mean, rstd, gamma, *, resid_grad=None, want_dx=True,
+                  dx_out: Optional[torch.Tensor] = None, want_bf16=False, row_scale=None, rows_per_group=1):
+    """Returns (dx fp32 or None, dx_bf16 or None).  dx = LN'(dy) + resid_grad."""
+    rows, C = x.shape
+    _require_cuda(dy, x)
+    dx = dx_out if dx_out is not None else (torch.empty((rows, C), device=x.device, dtype=F32) if want_dx else None)
+    dxb = torch.empty((rows, C), device=x.device, dtype=BF16) if want_bf16 else None
+    _lib.call("vsn_layernorm_bwd", _p(dy), dy.stride(0), 1 if dy.dtype == BF16 else 0, _p(x), x.stride(0),
+              _p(mean), _p(rstd), _p(gamma), _p(resid_grad), resid_grad.stride(0) if resid_grad is not None else 0,
+              _p(dx), dx.stride(0) if dx is not None else 0, _p(dxb), C, _p(row_scale), rows_per_group, rows, C,
+              _stream())
+    return dx, dxb
+
+
+def ln_param_grad(dy, x, mean, rstd, dgamma, dbeta) -> None:
+    rows, C = x.shape
+    _lib.call("vsn_colreduce", _p(dy), dy.stride(0), 1 if dy.dtype == BF16 else 0, _p(x), x.stride(0), _p(mean),
+              _p(rstd), _p(dgamma), _p(dbeta), rows, C, _stream())
+
+
+def colsum(dy: torch.Tensor, out: torch.Tensor) -> None:
+    """out[c] += sum_r dy[r, c]."""
+    rows, C = dy.shape
+    _lib.call("vsn_colreduce", _p(dy), dy.stride(0), 1 if dy.dtype == BF16 else 0, None, 0, None, None, None,
+              _p(out), rows, C, _stream())
+
+
+# ------------------------------------------------------------------ attention
+def _geom_tensor(geom: Sequence[int], device) -> torch.Tensor:
+    return torch.tensor(list(geom), dtype=torch.int32)  # host array; the ABI copies it by value
+
+
+class WindowGeom:
+    """Stage geometry handed to the attention kernels (host-side ints, kept alive as a ctypes array)."""
+
+    def __init__(self, B, grid, window, shift, use_mask):
+        import ctypes
+        self.B, self.grid, self.window, self.shift, self.use_mask = B, tuple(grid), tuple(window), tuple(shift), use_mask
+        vals = [B, *grid, *window, *shift, 1 if use_mask else 0]
+        self.arr = (ctypes.c_int * 11)(*vals)
+        self.S = B * (grid[0] // window[0]) * (grid[1] // window[1]) * (grid[2] // window[2])
+        self.N = window[0] * window[1] * window[2]
+
+
+def attn_fwd(qkv: torch.Tensor, heads: int, hd: int, *, S: int, N: int, scale: float,
+             geom: Optional[WindowGeom] = None, table: Optional[torch.Tensor] = None, want_lse: bool = True):
+    import ctypes
+    T = qkv.shape[0]
+    C = heads * hd
+    assert qkv.dtype == BF16 and qkv.is_contiguous() and qkv.shape[1] == 3 * C
+    _require_cuda(qkv)
+    out = torch.empty((T, C), device=qkv.device, dtype=BF16)
+    npad = (N + 63) // 64 * 64
+    lse = torch.empty((S, heads, npad), device=qkv.device, dtype=F32) if want_lse else None
+    _lib.call("vsn_attn_fwd", _p(qkv), _p(out), _p(lse), S, N, heads, hd, 1 if geom is not None else 0,
+              ctypes.cast(geom.arr, ctypes.c_void_p) if geom is not None else None, _p(table),
+              table.shape[0] if table is not None else 0, float(scale), _stream())
+    return out, lse
+
+
+def attn_bwd(qkv, out, dout, lse, heads: int, hd: int, *, S: int, N: int, scale: float,
+             geom: Optional[WindowGeom] = None, table: Optional[torch.Tensor] = None,
+             dtable: Optional[torch.Tensor] = None) -> torch.Tensor:
+    import ctypes
+    T = qkv.shape[0]
+    npad = (N + 63) // 64 * 64
+    assert dout.dtype == BF16 and dout.is_contiguous()
+    delta = torch.empty((S, heads, npad), device=qkv.device, dtype=F32)
+    dense = torch.zeros((heads, npad, npad), device=qkv.device, dtype=F32) if table is not None else None
+    # real tokens are all written by the kernels; padded-grid tokens always belong to a window too
+    dqkv = torch.empty_like(qkv)
+    _lib.call("vsn_attn_bwd", _p(qkv), _p(out), _p(dout), _p(lse), _p(delta), _p(dqkv), _p(dense), _p(dtable), S, N,
+              heads, hd, 1 if geom is not None else 0,
+              ctypes.cast(geom.arr, ctypes.c_void_p) if geom is not None else None, _p(table),
+              table.shape[0] if table is not None else 0, float(scale), _stream())
+    return dqkv
+
+
+# ------------------------------------------------------------------ layout kernels
+_IN_DTYPE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+def patch_gather(vol: torch.Tensor, patch: Sequence[int], *, out_dtype=BF16) -> torch.Tensor:
+    """vol [B,1,D,H,W] (fp32/fp16/bf16, contiguous) -> rows [B*gd*gh*gw, pd*ph*pw]."""
+    B, c, D, H, W = vol.shape
+    if c != 1:
+        raise NotImplementedError("vsn_b200 patch embedding supports in_channels=1 (the reference's MRI volumes)")
+    _require_cuda(vol)
+    pd, ph, pw = patch
+    gd, gh, gw = -(-D // pd), -(-H // ph), -(-W // pw)
+    out = torch.empty((B * gd * gh * gw, pd * ph * pw), device=vol.device, dtype=out_dtype)
+    _lib.call("vsn_patch_gather", _p(vol), _IN_DTYPE[vol.dtype], _p(out), 1 if out_dtype == BF16 else 0, B, D, H, W,
+              pd, ph, pw, _stream())
+    return out
+
+
+def grid_copy(src: torch.Tensor, sdims, ddims, B: int, C: int) -> torch.Tensor:
+    dst = torch.empty((B * ddims[0] * ddims[1] * ddims[2], C), device=src.device, dtype=F32)
+    _lib.call("vsn_grid_copy", _p(src), *sdims, _p(dst), *ddims, B, C, _stream())
+    return dst
+
+
+def merge_gather(x: torch.Tensor, pdims, rdims, B: int, C: int) -> torch.Tensor:
+    od = [(r + 1) // 2 for r in rdims]
+    out = torch.empty((B * od[0] * od[1] * od[2], 8 * C), device=x.device, dtype=F32)
+    _lib.call("vsn_merge_gather", _p(x), *pdims, *rdims, _p(out), B, C, 0, _stream())
+    return out
+
+
+def merge_scatter(dout: torch.Tensor, pdims, rdims, B: int, C: int) -> torch.Tensor:
+    dx = torch.zeros((B * pdims[0] * pdims[1] * pdims[2], C), device=dout.device, dtype=F32)
+    _lib.call("vsn_merge_gather", _p(dx), *pdims, *rdims, _p(dout), B, C, 1, _stream())
+    return dx
+
+
+def cast_rows_bf16(src: torch.Tensor, row_scale=None, rows_per_group=1) -> torch.Tensor:
+    rows, C = src.shape
+    assert src.dtype == F32 and src.is_contiguous()
+    dst = torch.empty((rows, C), device=src.device, dtype=BF16)
+    _lib.call("vsn_cast_rows_bf16", _p(src), _p(dst), _p(row_scale), rows_per_group, rows, C, _stream())
+    return dst
+
+
+def cast_bf16(src: torch.Tensor, dst: Optional[torch.Tensor] = None) -> torch.Tensor:
+    assert src.dtype == F32 and src.is_contiguous()
+    if dst is None:
+        dst = torch.empty(src.shape, device=src.device, dtype=BF16)
+    _require_cuda(src)
+    _lib.call("vsn_cast_bf16", _p(src), _p(dst), src.numel(), _stream())
+    return dst
+
+
+def token_mean(x: torch.Tensor, B: int, T: int, C: int) -> torch.Tensor:
+    out = torch.empty((B, C), device=x.device, dtype=F32)
+    _lib.call("vsn_token_mean", _p(x), _p(out), B, T, C, 0, _stream())
+    return out
+
+
+def token_mean_bwd(dout: torch.Tensor, B: int, T: int, C: int) -> torch.Tensor:
+    dx = torch.empty((B * T, C), device=dout.device, dtype=F32)
+    _lib.call("vsn_token_mean", _p(dout), _p(dx), B, T, C, 1, _stream())
+    return dx
+
+
+def head_fwd(feat: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    B, Fdim = feat.shape
+    K = W.shape[0]
+    _require_cuda(feat)
+    out = torch.empty((B, K), device=feat.device, dtype=F32)
+    _lib.call("vsn_head_fwd", _p(feat), _p(W), _p(bias), _p(out), B, K, Fdim, _stream())
+    return out
+
+
+def head_bwd(dlogits, feat, W, dW, db) -> torch.Tensor:
+    B, Fdim = feat.shape
+    K = W.shape[0]
+    dfeat = torch.empty_like(feat)
+    _lib.call("vsn_head_bwd", _p(dlogits), _p(feat), _p(W), _p(dfeat), _p(dW), _p(db), B, K, Fdim, _stream())
+    return dfeat
+
+
+def vit_assemble(emb, cls, pos, B: int, T: int, C: int) -> torch.Tensor:
+    x = torch.empty((B * (T + 1), C), device=emb.device, dtype=F32)
+    _lib.call("vsn_vit_assemble", _p(emb), _p(cls), _p(pos), _p(x), B, T, C, _stream())
+    return x
+
+
+def vit_assemble_bwd(dx, dcls, dpos, B: int, T: int, C: int) -> None:
+    _lib.call("vsn_vit_assemble_bwd", _p(dx), _p(dcls), _p(dpos), B, T, C, _stream())
