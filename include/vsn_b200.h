@@ -126,6 +126,10 @@ int vsn_mt_ema(const long long* p_ptrs, const long long* new_ptrs, const long lo
                const long long* ema_ptrs, const long long* sizes, const int* chunk_tensor, const long long* chunk_off,
                int n_chunks, float w0, float w1, float w2, void* stream);
 
+/* dst_bf16[t] = bf16(src_fp32[t]): refreshes the bf16 copies of the GEMM weights once per forward. */
+int vsn_mt_cast_bf16(const long long* src_ptrs, const long long* dst_ptrs, const long long* sizes,
+                     const int* chunk_tensor, const long long* chunk_off, int n_chunks, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

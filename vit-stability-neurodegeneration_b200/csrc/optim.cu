@@ -146,7 +146,26 @@ __global__ void __launch_bounds__(MT_THREADS) mt_ema_kernel(const long long* p_p
   }
 }
 
+// dst_bf16 = bf16(src_fp32) per tensor: the bf16 shadow of the GEMM weights
+__global__ void __launch_bounds__(MT_THREADS) mt_cast_bf16_kernel(const long long* src_ptrs, const long long* dst_ptrs,
+                                                                  MTTable tab) {
+  int tensor; long long off, n;
+  if (!chunk_span(tab, tensor, off, n)) return;
+  const float* s = reinterpret_cast<const float*>(src_ptrs[tensor]) + off;
+  bf16* d = reinterpret_cast<bf16*>(dst_ptrs[tensor]) + off;
+  for (long long i = threadIdx.x; i < n; i += MT_THREADS) d[i] = __float2bfloat16(s[i]);
+}
+
 }  // namespace
+
+extern "C" int vsn_mt_cast_bf16(const long long* src_ptrs, const long long* dst_ptrs, const long long* sizes,
+                                const int* chunk_tensor, const long long* chunk_off, int n_chunks, void* stream) {
+  if (n_chunks == 0) return 0;
+  MTTable t{sizes, chunk_tensor, chunk_off};
+  mt_cast_bf16_kernel<<<n_chunks, MT_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src_ptrs, dst_ptrs, t);
+  VSN_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int vsn_mt_chunk_elems() { return MT_CHUNK; }
 

@@ -1,0 +1,316 @@
+"""SAM and EMA on top of the multi-tensor kernels (csrc/optim.cu).
+
+`SAM` and `EMAModel` keep the constructor / method surface of the reference's
+`regularization/sam.py` and `utils/ema.py`, so `train/train_transformer.py` drives them unchanged; the
+per-parameter Python loops, `.clone()`s, host syncs and the D2H copy of the whole state_dict that the
+reference performs every step are replaced by a handful of kernel launches over pointer tables.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple, Type
+
+import torch
+
+from . import _lib
+
+F32 = torch.float32
+
+
+def build_chunks(sizes: Sequence[int], chunk: int) -> Tuple[List[int], List[int]]:
+    """Host-side chunk table: every tensor is cut into pieces of `chunk` elements.
+    Returns (chunk_tensor, chunk_offset)."""
+    ct, co = [], []
+    for t, n in enumerate(sizes):
+        off = 0
+        while off < n:
+            ct.append(t)
+            co.append(off)
+            off += chunk
+    return ct, co
+
+
+class MultiTensorTable:
+    """Device-side description of a list of same-shaped tensor lists (sizes + chunk table)."""
+
+    def __init__(self, like: Sequence[torch.Tensor], device):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("vsn_b200 multi-tensor kernels need CUDA tensors (there is no CPU fallback)")
+        _lib.check_device()
+        self.n = len(like)
+        self.sizes_host = [int(t.numel()) for t in like]
+        chunk = _lib.load().vsn_mt_chunk_elems()
+        ct, co = build_chunks(self.sizes_host, chunk)
+        self.n_chunks = len(ct)
+        self.sizes = torch.tensor(self.sizes_host, dtype=torch.int64, device=self.device)
+        self.chunk_tensor = torch.tensor(ct, dtype=torch.int32, device=self.device)
+        self.chunk_off = torch.tensor(co, dtype=torch.int64, device=self.device)
+
+    def ptr_array(self, tensors: Sequence[torch.Tensor]) -> torch.Tensor:
+        assert len(tensors) == self.n
+        for t, n in zip(tensors, self.sizes_host):
+            if t.numel() != n or not t.is_contiguous() or not t.is_cuda:
+                raise RuntimeError("multi-tensor kernels need contiguous CUDA tensors of matching sizes")
+        return torch.tensor([t.data_ptr() for t in tensors], dtype=torch.int64, device=self.device)
+
+    def _tab(self):
+        return self.sizes.data_ptr(), self.chunk_tensor.data_ptr(), self.chunk_off.data_ptr(), self.n_chunks
+
+    @staticmethod
+    def _stream():
+        return torch.cuda.current_stream().cuda_stream
+
+    def sqnorm(self, g_ptrs, p_ptrs, sq, adaptive):
+        _lib.call("vsn_mt_sqnorm", g_ptrs.data_ptr(), p_ptrs.data_ptr() if p_ptrs is not None else None, *self._tab(),
+                  sq.data_ptr(), int(adaptive), self._stream())
+
+    def sam_perturb(self, p_ptrs, g_ptrs, old_ptrs, scale, flags, adaptive):
+        _lib.call("vsn_mt_sam_perturb", p_ptrs.data_ptr(), g_ptrs.data_ptr(), old_ptrs.data_ptr(), *self._tab(),
+                  scale.data_ptr(), flags.data_ptr(), int(adaptive), self._stream())
+
+    def copy(self, dst_ptrs, src_ptrs):
+        _lib.call("vsn_mt_copy", dst_ptrs.data_ptr(), src_ptrs.data_ptr(), *self._tab(), self._stream())
+
+    def cast_bf16(self, src_ptrs, dst_ptrs):
+        _lib.call("vsn_mt_cast_bf16", src_ptrs.data_ptr(), dst_ptrs.data_ptr(), *self._tab(), self._stream())
+
+    def ema(self, p_ptrs, new_ptrs, s0_ptrs, s1_ptrs, ema_ptrs, w0, w1, w2):
+        _lib.call("vsn_mt_ema", p_ptrs.data_ptr(), new_ptrs.data_ptr(),
+                  s0_ptrs.data_ptr() if s0_ptrs is not None else None,
+                  s1_ptrs.data_ptr() if s1_ptrs is not None else None, ema_ptrs.data_ptr(), *self._tab(),
+                  float(w0), float(w1), float(w2), self._stream())
+
+
+class SAM(torch.optim.Optimizer):
+    """Sharpness-Aware Minimization with the reference's API (regularization/sam.py:9-165).
+
+    first_step: global gradient norm + `old_p = p; p += rho/(||g||+1e-12) * g` in three launches, no host
+    synchronisation.  second_step: `p = old_p` (one launch) then the base optimiser's step.
+    Non-finite handling follows the reference: tensors with a non-finite norm are left out of the norm and
+    not perturbed; a zero norm disables the perturbation.  (Where the reference returns early without saving
+    `old_p` and would later restore a stale copy, this implementation saves `old_p = p`, so second_step is
+    always well defined.)"""
+
+    def __init__(self, params, base_optimizer: Type[torch.optim.Optimizer], rho: float = 0.05,
+                 adaptive: bool = False, **kwargs):
+        assert rho >= 0.0, f"Invalid rho, should be non-negative: {rho}"
+        defaults = dict(rho=rho, adaptive=adaptive, **kwargs)
+        super().__init__(params, defaults)
+        self.base_optimizer = base_optimizer(self.param_groups, **kwargs)
+        self.param_groups = self.base_optimizer.param_groups
+        self.defaults.update(self.base_optimizer.defaults)
+        self._plan_key = None
+        self._plan = None
+
+    # -- plan: pointer tables for the parameters that currently have a gradient ------------------
+    def _active(self) -> List[torch.nn.Parameter]:
+        ps = [p for g in self.param_groups for p in g["params"] if p.grad is not None]
+        rhos = {g["rho"] for g in self.param_groups}
+        ads = {bool(g["adaptive"]) for g in self.param_groups}
+        if len(rhos) > 1 or len(ads) > 1:
+            raise NotImplementedError("vsn_b200 SAM expects one rho / adaptive setting for all parameter groups")
+        return ps
+
+    def _get_plan(self, ps: List[torch.nn.Parameter]):
+        key = tuple((p.data_ptr(), p.numel()) for p in ps)
+        if key != self._plan_key:
+            for p in ps:
+                if p.dtype != F32 or not p.is_cuda:
+                    raise RuntimeError("vsn_b200 SAM needs fp32 CUDA parameters (there is no CPU fallback)")
+                if not p.is_contiguous():
+                    raise RuntimeError("vsn_b200 SAM needs contiguous parameters")
+            dev = ps[0].device
+            tab = MultiTensorTable([p.detach() for p in ps], dev)
+            olds = []
+            for p in ps:
+                st = self.state[p]
+                if "old_p" not in st or st["old_p"].shape != p.shape or st["old_p"].device != p.device:
+                    st["old_p"] = torch.empty_like(p.detach(), memory_format=torch.contiguous_format)
+                olds.append(st["old_p"])
+            self._plan = dict(tab=tab, p=tab.ptr_array([p.detach() for p in ps]), old=tab.ptr_array(olds),
+                              gkey=None, g=None,
+                              sq=torch.zeros(len(ps), device=dev, dtype=F32),
+                              flags=torch.zeros(len(ps), device=dev, dtype=torch.int32),
+                              scale=torch.zeros(2, device=dev, dtype=F32))
+            self._plan_key = key
+        pl = self._plan
+        gkey = tuple(p.grad.data_ptr() for p in ps)
+        if gkey != pl["gkey"]:
+            pl["g"] = pl["tab"].ptr_array([p.grad for p in ps])
+            pl["gkey"] = gkey
+        return pl
+
+    @torch.no_grad()
+    def _grad_norm(self) -> torch.Tensor:
+        ps = self._active()
+        if not ps:
+            dev = self.param_groups[0]["params"][0].device
+            return torch.tensor(1e-12, device=dev)
+        pl = self._get_plan(ps)
+        self._launch_norm(pl)
+        return pl["scale"][1].clone()
+
+    def _launch_norm(self, pl) -> None:
+        adaptive = bool(self.param_groups[0]["adaptive"])
+        pl["sq"].zero_()
+        pl["tab"].sqnorm(pl["g"], pl["p"] if adaptive else None, pl["sq"], adaptive)
+        _lib.call("vsn_sam_scale", pl["sq"].data_ptr(), len(pl["sq"]), float(self.param_groups[0]["rho"]),
+                  pl["scale"].data_ptr(), pl["flags"].data_ptr(), torch.cuda.current_stream().cuda_stream)
+
+    @torch.no_grad()
+    def first_step(self, zero_grad: bool = False) -> None:
+        ps = self._active()
+        if ps:
+            pl = self._get_plan(ps)
+            self._launch_norm(pl)
+            pl["tab"].sam_perturb(pl["p"], pl["g"], pl["old"], pl["scale"], pl["flags"],
+                                  bool(self.param_groups[0]["adaptive"]))
+            self._perturbed = ps
+        else:
+            self._perturbed = []
+        if zero_grad:
+            self.zero_grad()
+
+    @torch.no_grad()
+    def second_step(self, zero_grad: bool = False, scaler=None) -> None:
+        ps = [p for g in self.param_groups for p in g["params"] if p.grad is not None and "old_p" in self.state[p]]
+        if ps:
+            pl = self._get_plan(ps)
+            pl["tab"].copy(pl["p"], pl["old"])     # back to "w" from "w + e(w)"
+        if scaler is None:
+            self.base_optimizer.step()
+            if zero_grad:
+                self.zero_grad()
+        else:
+            scaler.step(self.base_optimizer)
+            scaler.update()
+            if zero_grad:
+                self.zero_grad()
+
+    @torch.no_grad()
+    def step(self, closure: Optional[Callable[[], Any]] = None) -> None:
+        assert closure is not None, "Sharpness Aware Minimization requires closure, but it was not provided"
+        closure = torch.enable_grad()(closure)
+        self.first_step(zero_grad=True)
+        closure()
+        self.second_step()
+
+    def load_state_dict(self, state_dict: Dict[str, Any]) -> None:
+        super().load_state_dict(state_dict)
+        self.base_optimizer.param_groups = self.param_groups
+
+
+class EMAModel:
+    """Weighted average of the last `n_models` parameter snapshots, API of utils/ema.py:10-178.
+
+    The reference copies the whole state_dict to the host every step and averages there; here the snapshot
+    ring and the average live on the device and one kernel both takes the new snapshot and recomputes the
+    average (`ema = sum_i w_i * s_i`, `w_i = decay^(k-1-i) / sum_j decay^j`, oldest first, fma order of
+    `Tensor.add_(state, alpha=w)`).  Non-floating buffers follow the newest snapshot.  `model_state` is the
+    same name -> tensor mapping (device tensors) and is what the trainer stores as the checkpoint's "model"."""
+
+    def __init__(self, model: torch.nn.Module, decay: float, n_models: int = 3,
+                 device: Optional[torch.device] = None):
+        if not 1 <= n_models <= 3:
+            raise NotImplementedError("vsn_b200 EMAModel supports n_models in 1..3 (the trainer always uses 3)")
+        self.decay = decay
+        self.n_models = n_models
+        self.device = device or next(model.parameters()).device
+        sd = model.state_dict()
+        self._fkeys = [k for k, v in sd.items() if v.is_floating_point()]
+        self._okeys = [k for k, v in sd.items() if not v.is_floating_point()]
+        live = [sd[k] for k in self._fkeys]
+        for v in live:
+            if not v.is_cuda or v.dtype != F32:
+                raise RuntimeError("vsn_b200 EMAModel needs an fp32 CUDA model (there is no CPU fallback)")
+        self._table = MultiTensorTable(live, live[0].device)
+        mk = lambda: [torch.empty_like(v, memory_format=torch.contiguous_format) for v in live]  # noqa: E731
+        self._slots = [mk()]
+        self._slot_ptrs = [self._table.ptr_array(self._slots[0])]
+        self._order = [0]                       # live snapshots, oldest first (indices into _slots)
+        ema = mk()
+        self._ema_ptrs = self._table.ptr_array(ema)
+        self.model_state: Dict[str, torch.Tensor] = {}
+        for k, e in zip(self._fkeys, ema):
+            self.model_state[k] = e
+        for k in self._okeys:
+            self.model_state[k] = sd[k].detach().clone()
+        # initial state counts as the first snapshot (utils/ema.py:41-48)
+        self._live_key = None
+        self._table.ema(self._live_ptrs(sd), self._slot_ptrs[0], None, None, self._ema_ptrs, 0.0, 0.0, 1.0)
+        self.collected_params: dict = {}
+        self.orig_state = None
+        self._stash = None
+
+    def _live_ptrs(self, sd) -> torch.Tensor:
+        key = tuple(sd[k].data_ptr() for k in self._fkeys)
+        if key != self._live_key:
+            self._live_key = key
+            self._live = self._table.ptr_array([sd[k].detach() for k in self._fkeys])
+        return self._live
+
+    @torch.no_grad()
+    def update(self, model: torch.nn.Module) -> None:
+        sd = model.state_dict()
+        if len(self._order) < self.n_models:
+            self._slots.append([torch.empty_like(v) for v in self._slots[0]])
+            self._slot_ptrs.append(self._table.ptr_array(self._slots[-1]))
+            new = len(self._slots) - 1
+            older = list(self._order)
+        else:
+            new = self._order[0]                # evicted snapshot's storage is recycled
+            older = self._order[1:]
+        k = len(older) + 1
+        w = [self.decay ** i for i in range(k)][::-1]
+        tot = sum(w)
+        w = [x / tot for x in w]
+        s0 = self._slot_ptrs[older[-2]] if len(older) >= 2 else None
+        s1 = self._slot_ptrs[older[-1]] if len(older) >= 1 else None
+        w0 = w[-3] if len(older) >= 2 else 0.0
+        w1 = w[-2] if len(older) >= 1 else 0.0
+        self._table.ema(self._live_ptrs(sd), self._slot_ptrs[new], s0, s1, self._ema_ptrs, w0, w1, w[-1])
+        self._order = older + [new]
+        for name in self._okeys:
+            self.model_state[name].copy_(sd[name])
+
+    @torch.no_grad()
+    def apply_to(self, model: torch.nn.Module) -> None:
+        if self.model_state is None:
+            return
+        sd = model.state_dict()
+        if self._stash is None:
+            self._stash = [torch.empty_like(v) for v in self._slots[0]]
+            self._stash_ptrs = self._table.ptr_array(self._stash)
+        live = self._live_ptrs(sd)
+        self._table.copy(self._stash_ptrs, live)
+        self.orig_state = {k: s for k, s in zip(self._fkeys, self._stash)}
+        for k in self._okeys:
+            self.orig_state[k] = sd[k].detach().clone()
+        self._table.copy(live, self._ema_ptrs)
+        for k in self._okeys:
+            sd[k].copy_(self.model_state[k])
+
+    @torch.no_grad()
+    def restore(self, model: torch.nn.Module) -> None:
+        if self.orig_state is None:
+            return
+        sd = model.state_dict()
+        self._table.copy(self._live_ptrs(sd), self._stash_ptrs)
+        for k in self._okeys:
+            sd[k].copy_(self.orig_state[k])
+        self.orig_state = None
+
+    @torch.no_grad()
+    def update_bn_stats(self, model: torch.nn.Module, data_loader) -> None:
+        """utils/ema.py:144-178 — only meaningful for BatchNorm models (not on the Swin/ViT path)."""
+        original_state = copy.deepcopy(model.state_dict())
+        self.apply_to(model)
+        model.train()
+        for x, _ in data_loader:
+            model(x.to(next(model.parameters()).device))
+        for name, param in model.state_dict().items():
+            if "running_" in name or "batch_norm" in name:
+                self.model_state[name].copy_(param)
+        model.load_state_dict(original_state)
+        self.orig_state = None

@@ -1,0 +1,302 @@
+"""Swin-3D forward/backward built from the vsn_b200 kernels.
+
+The residual stream is an fp32 token matrix `[B*Dp*Hp*Wp, C]` in natural (b,d,h,w) order on the
+*padded* stage grid (the reference pads once per stage and keeps the padded tokens alive,
+models/swin_transformer_3d.py:457-461,508).  GEMM operands are bf16, accumulation / LayerNorm /
+softmax statistics are fp32.  Each autograd.Function below is one unit of the reference's module tree
+with its backward written by hand on top of the same C ABI (no autograd through torch ops).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+
+F32, BF16 = torch.float32, torch.bfloat16
+
+
+def _contig_f32(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != F32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# --------------------------------------------------------------------------------------
+# bf16 shadow of the GEMM weights (one flat buffer, refreshed by one kernel per forward)
+# --------------------------------------------------------------------------------------
+class WeightShadow:
+    """bf16 copies of the fp32 master weights that feed tensor-core GEMMs.
+
+    The copies live in one flat buffer and are refreshed with a single multi-tensor launch at the start
+    of every model forward, so they can never be stale with respect to optimiser / SAM / EMA writes
+    (which bypass torch's version counters when they come from our own kernels)."""
+
+    def __init__(self, params: Sequence[torch.nn.Parameter]):
+        self.params = list(params)
+        self._key = None
+        self._flat = None
+        self._views: List[torch.Tensor] = []
+        self._table = None
+
+    def refresh(self) -> None:
+        from .optim import MultiTensorTable
+        key = tuple((p.data_ptr(), p.numel()) for p in self.params)
+        if key != self._key:
+            dev = self.params[0].device
+            sizes = [(p.numel() + 7) // 8 * 8 for p in self.params]   # keep every view 16-byte aligned
+            self._flat = torch.empty(sum(sizes), device=dev, dtype=BF16)
+            self._views, off = [], 0
+            for p, s in zip(self.params, sizes):
+                self._views.append(self._flat[off: off + p.numel()].view(p.shape[0], -1))
+                off += s
+            self._table = MultiTensorTable([p.detach() for p in self.params], dev)
+            self._dst_ptrs = self._table.ptr_array(self._views)
+            self._src_ptrs = self._table.ptr_array([p.detach() for p in self.params])
+            self._key = key
+        self._table.cast_bf16(self._src_ptrs, self._dst_ptrs)
+
+    def view(self, i: int) -> torch.Tensor:
+        return self._views[i]
+
+
+# --------------------------------------------------------------------------------------
+# per-unit autograd Functions
+# --------------------------------------------------------------------------------------
+@dataclass
+class BlockCfg:
+    heads: int
+    hd: int
+    geom: Optional[ops.WindowGeom]  # window geometry incl. shift / mask flag; None = dense (ViT) attention
+    tokens_per_sample: int
+    S: int = 0                      # sequences (windows or samples) and tokens per sequence
+    N: int = 0
+    w16: Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor] = None   # qkv, proj, fc1, fc2 (bf16)
+    scale1: Optional[torch.Tensor] = None   # DropPath keep/(1-p) per sample for the attention branch
+    scale2: Optional[torch.Tensor] = None   # ... for the MLP branch
+
+
+class SwinBlockFn(torch.autograd.Function):
+    """One pre-norm transformer block: SwinTransformerBlock.forward (models/swin_transformer_3d.py:328-380) with
+    window attention, or the ViT block (models/vit_3d.py:129-142,237-254) with dense attention (geom None,
+    no qkv bias, no bias table)."""
+
+    @staticmethod
+    def forward(ctx, x, n1w, n1b, qkv_w, qkv_b, table, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b,
+                cfg: BlockCfg):
+        x = _contig_f32(x)
+        wq, wp, w1, w2 = cfg.w16
+        g, tps = cfg.geom, cfg.tokens_per_sample
+        S, N = (g.S, g.N) if g is not None else (cfg.S, cfg.N)
+        y1, mean1, rstd1 = ops.layernorm_fwd(x, n1w, n1b)
+        qkv = ops.linear_fwd(y1, wq, qkv_b)
+        o, lse = ops.attn_fwd(qkv, cfg.heads, cfg.hd, S=S, N=N, scale=cfg.hd ** -0.5, geom=g, table=table)
+        x1 = ops.linear_fwd(o, wp, proj_b, out_dtype=F32, resid=x, row_scale=cfg.scale1, rows_per_group=tps)
+        y2, mean2, rstd2 = ops.layernorm_fwd(x1, n2w, n2b)
+        h = torch.empty((x.shape[0], w1.shape[0]), device=x.device, dtype=BF16)
+        a = ops.linear_fwd(y2, w1, fc1_b, gelu_aux=h)
+        x2 = ops.linear_fwd(a, w2, fc2_b, out_dtype=F32, resid=x1, row_scale=cfg.scale2, rows_per_group=tps)
+        ctx.cfg = cfg
+        ctx.has_qkv_bias = qkv_b is not None
+        ctx.has_table = table is not None
+        ctx.save_for_backward(x, mean1, rstd1, y1, qkv, o, lse, x1, mean2, rstd2, y2, h, a, n1w, n2w,
+                              table if table is not None else n1w)
+        ctx.shapes = (qkv_w.shape, proj_w.shape, fc1_w.shape, fc2_w.shape)
+        return x2
+
+    @staticmethod
+    def backward(ctx, g):
+        cfg: BlockCfg = ctx.cfg
+        x, mean1, rstd1, y1, qkv, o, lse, x1, mean2, rstd2, y2, h, a, n1w, n2w, table = ctx.saved_tensors
+        wq, wp, w1, w2 = cfg.w16
+        geom, tps = cfg.geom, cfg.tokens_per_sample
+        S, N = (geom.S, geom.N) if geom is not None else (cfg.S, cfg.N)
+        if not ctx.has_table:
+            table = None
+        dev = x.device
+        C = x.shape[1]
+        g = _contig_f32(g)
+        z = lambda *s: torch.zeros(s, device=dev, dtype=F32)  # noqa: E731
+        d_qkv_w, d_proj_w, d_fc1_w, d_fc2_w = (z(*s) for s in ctx.shapes)
+        d_qkv_b, d_proj_b, d_fc1_b, d_fc2_b = z(ctx.shapes[0][0]), z(C), z(w1.shape[0]), z(C)
+        d_n1w, d_n1b, d_n2w, d_n2b = z(C), z(C), z(C), z(C)
+        d_table = torch.zeros_like(table) if table is not None else None
+        # ---- MLP branch: x2 = x1 + s2 * (W2 gelu(W1 LN2(x1) + b1) + b2)
+        gs = ops.cast_rows_bf16(g, cfg.scale2, tps)
+        ops.colsum(gs, d_fc2_b)
+        ops.linear_wgrad(gs, a, d_fc2_w)
+        dh = ops.linear_dgrad(gs, w2, gelu_aux=h)
+        ops.colsum(dh, d_fc1_b)
+        ops.linear_wgrad(dh, y2, d_fc1_w)
+        dy2 = ops.linear_dgrad(dh, w1)
+        ops.ln_param_grad(dy2, x1, mean2, rstd2, d_n2w, d_n2b)
+        g1, g1s = ops.layernorm_bwd(dy2, x1, mean2, rstd2, n2w, resid_grad=g, want_bf16=True, row_scale=cfg.scale1,
+                                    rows_per_group=tps)
+        # ---- attention branch: x1 = x + s1 * (Wp attn(Wq LN1(x) + bq) + bp)
+        ops.colsum(g1s, d_proj_b)
+        ops.linear_wgrad(g1s, o, d_proj_w)
+        do = ops.linear_dgrad(g1s, wp)
+        dqkv = ops.attn_bwd(qkv, o, do, lse, cfg.heads, cfg.hd, S=S, N=N, scale=cfg.hd ** -0.5, geom=geom,
+                            table=table, dtable=d_table)
+        if ctx.has_qkv_bias:
+            ops.colsum(dqkv, d_qkv_b)
+        ops.linear_wgrad(dqkv, y1, d_qkv_w)
+        dy1 = ops.linear_dgrad(dqkv, wq)
+        ops.ln_param_grad(dy1, x, mean1, rstd1, d_n1w, d_n1b)
+        g0, _ = ops.layernorm_bwd(dy1, x, mean1, rstd1, n1w, resid_grad=g1, dx_out=g1)
+        return (g0, d_n1w, d_n1b, d_qkv_w, d_qkv_b if ctx.has_qkv_bias else None, d_table, d_proj_w, d_proj_b,
+                d_n2w, d_n2b, d_fc1_w, d_fc1_b, d_fc2_w, d_fc2_b, None)
+
+
+class PatchEmbedFn(torch.autograd.Function):
+    """PatchEmbed3D.forward: pad + Conv3d(k=s=patch) + LayerNorm (models/swin_transformer_3d.py:532-543)."""
+
+    @staticmethod
+    def forward(ctx, vol, conv_w, conv_b, nw, nb, w16, patch):
+        rows = ops.patch_gather(vol, patch)                                    # bf16 [T, pd*ph*pw]
+        y = ops.linear_fwd(rows, w16, conv_b, out_dtype=F32)                   # conv output, fp32 [T, C]
+        if nw is None:
+            ctx.has_norm = False
+            ctx.save_for_backward(rows)
+            ctx.wshape = conv_w.shape
+            return y
+        x0, mean, rstd = ops.layernorm_fwd(y, nw, nb, out_dtype=F32)
+        ctx.has_norm = True
+        ctx.save_for_backward(rows, y, mean, rstd, nw)
+        ctx.wshape = conv_w.shape
+        return x0
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _contig_f32(g)
+        dev = g.device
+        C = g.shape[1]
+        d_w = torch.zeros((C, ctx.wshape.numel() // C), device=dev, dtype=F32)
+        d_b = torch.zeros(C, device=dev, dtype=F32)
+        if ctx.has_norm:
+            rows, y, mean, rstd, nw = ctx.saved_tensors
+            d_nw, d_nb = torch.zeros(C, device=dev, dtype=F32), torch.zeros(C, device=dev, dtype=F32)
+            ops.ln_param_grad(g, y, mean, rstd, d_nw, d_nb)
+            _, dyb = ops.layernorm_bwd(g, y, mean, rstd, nw, want_dx=False, want_bf16=True)
+        else:
+            (rows,) = ctx.saved_tensors
+            d_nw = d_nb = None
+            dyb = ops.cast_rows_bf16(g)
+        ops.colsum(dyb, d_b)
+        ops.linear_wgrad(dyb, rows, d_w)
+        return None, d_w.view(ctx.wshape), d_b, d_nw, d_nb, None, None
+
+
+class GridCopyFn(torch.autograd.Function):
+    """Zero-pad to the window multiple / crop back (models/swin_transformer_3d.py:457-461,508)."""
+
+    @staticmethod
+    def forward(ctx, x, sdims, ddims, B):
+        ctx.meta = (sdims, ddims, B, x.shape[1])
+        return ops.grid_copy(_contig_f32(x), sdims, ddims, B, x.shape[1])
+
+    @staticmethod
+    def backward(ctx, g):
+        sdims, ddims, B, C = ctx.meta
+        return ops.grid_copy(_contig_f32(g), ddims, sdims, B, C), None, None, None
+
+
+class PatchMergeFn(torch.autograd.Function):
+    """Crop + PatchMerging: gather 2x2x2 neighbours, LayerNorm(8C), Linear(8C,2C,bias=False)
+    (models/swin_transformer_3d.py:508,553-572).  x lives on the padded stage grid."""
+
+    @staticmethod
+    def forward(ctx, x, nw, nb, red_w, w16, pdims, rdims, B):
+        x = _contig_f32(x)
+        C = x.shape[1]
+        xg = ops.merge_gather(x, pdims, rdims, B, C)
+        y, mean, rstd = ops.layernorm_fwd(xg, nw, nb)
+        out = ops.linear_fwd(y, w16, None, out_dtype=F32)
+        ctx.meta = (pdims, rdims, B, C, red_w.shape, w16)
+        ctx.save_for_backward(xg, mean, rstd, y, nw)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        pdims, rdims, B, C, wshape, w16 = ctx.meta
+        xg, mean, rstd, y, nw = ctx.saved_tensors
+        dev = g.device
+        gb = ops.cast_rows_bf16(_contig_f32(g))
+        d_w = torch.zeros(wshape, device=dev, dtype=F32)
+        ops.linear_wgrad(gb, y, d_w)
+        dy = ops.linear_dgrad(gb, w16)
+        d_nw, d_nb = torch.zeros(8 * C, device=dev, dtype=F32), torch.zeros(8 * C, device=dev, dtype=F32)
+        ops.ln_param_grad(dy, xg, mean, rstd, d_nw, d_nb)
+        dxg, _ = ops.layernorm_bwd(dy, xg, mean, rstd, nw)
+        dx = ops.merge_scatter(dxg, pdims, rdims, B, C)
+        return dx, d_nw, d_nb, d_w, None, None, None, None
+
+
+class NormPoolHeadFn(torch.autograd.Function):
+    """backbone.norm + AdaptiveAvgPool3d(1) + flatten + head Linear
+    (models/swin_transformer_3d.py:692-698,758-761).  x: [B*T, F] on the real (cropped) grid."""
+
+    @staticmethod
+    def forward(ctx, x, nw, nb, head_w, head_b, B, T):
+        x = _contig_f32(x)
+        Fd = x.shape[1]
+        y, mean, rstd = ops.layernorm_fwd(x, nw, nb, out_dtype=F32)
+        pooled = ops.token_mean(y, B, T, Fd)
+        ctx.meta = (B, T, Fd, head_w is not None, head_b is not None)
+        if head_w is None:
+            ctx.save_for_backward(x, mean, rstd, nw)
+            return pooled
+        logits = ops.head_fwd(pooled, head_w, head_b)
+        ctx.save_for_backward(x, mean, rstd, nw, pooled, head_w)
+        return logits
+
+    @staticmethod
+    def backward(ctx, g):
+        B, T, Fd, has_head, has_bias = ctx.meta
+        g = _contig_f32(g)
+        dev = g.device
+        if has_head:
+            x, mean, rstd, nw, pooled, head_w = ctx.saved_tensors
+            d_hw = torch.zeros_like(head_w)
+            d_hb = torch.zeros(head_w.shape[0], device=dev, dtype=F32)
+            dfeat = ops.head_bwd(g, pooled, head_w, d_hw, d_hb)
+        else:
+            x, mean, rstd, nw = ctx.saved_tensors
+            d_hw = d_hb = None
+            dfeat = g
+        dy = ops.token_mean_bwd(dfeat, B, T, Fd)
+        d_nw, d_nb = torch.zeros(Fd, device=dev, dtype=F32), torch.zeros(Fd, device=dev, dtype=F32)
+        ops.ln_param_grad(dy, x, mean, rstd, d_nw, d_nb)
+        dx, _ = ops.layernorm_bwd(dy, x, mean, rstd, nw)
+        return dx, d_nw, d_nb, d_hw, (d_hb if has_bias else None), None, None
+
+
+# --------------------------------------------------------------------------------------
+# helpers shared by the drop-in modules
+# --------------------------------------------------------------------------------------
+def padded_dims(real: Sequence[int], window: Sequence[int]) -> Tuple[int, int, int]:
+    return tuple((r + w - 1) // w * w for r, w in zip(real, window))
+
+
+def relative_position_index(window: Sequence[int]) -> torch.Tensor:
+    """int64 [N,N] buffer kept only for state_dict compatibility (the kernels use the closed form
+    idx = lin(i) - lin(j) + offset; models/swin_transformer_3d.py:132-152)."""
+    wd, wh, ww = window
+    t = torch.arange(wd * wh * ww)
+    lin = (t // (wh * ww)) * ((2 * wh - 1) * (2 * ww - 1)) + ((t // ww) % wh) * (2 * ww - 1) + (t % ww)
+    off = (wd - 1) * (2 * wh - 1) * (2 * ww - 1) + (wh - 1) * (2 * ww - 1) + (ww - 1)
+    return (lin[:, None] - lin[None, :] + off).to(torch.int64)
+
+
+def droppath_scale(p: float, B: int, device, training: bool, forced=None) -> Optional[torch.Tensor]:
+    """Per-sample keep/(1-p) factors (timm DropPath semantics); None = identity."""
+    if p == 0.0 or not training:
+        return None
+    keep = 1.0 - p
+    if forced is not None:
+        m = next(forced).to(device=device, dtype=F32)
+    else:
+        m = torch.empty(B, device=device, dtype=F32).bernoulli_(keep)
+    return (m / keep).contiguous()
