@@ -26,6 +26,8 @@ extern "C" {
 int vsn_version(void);
 const char* vsn_last_error(void);
 int vsn_check_device(void);
+/* kernel launches issued by the library since it was loaded (bench.py's gpu_launches counter) */
+long long vsn_launch_count(void);
 
 /* ---- tcgen05 GEMM with fused epilogue ---------------------------------------------------------
  * out[M,N] = epilogue( alpha * sum_k A(m,k) * B(n,k) )

@@ -58,6 +58,8 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)  # AttributeError if the ABI and the binding disagree
             fn.argtypes = args
             fn.restype = C.c_int
+        lib.vsn_launch_count.argtypes = []
+        lib.vsn_launch_count.restype = C.c_longlong
         lib.vsn_last_error.argtypes = []
         lib.vsn_last_error.restype = C.c_char_p
         _lib = lib
@@ -66,6 +68,10 @@ def load() -> C.CDLL:
 
 def last_error() -> str:
     return load().vsn_last_error().decode("utf-8", "replace")
+
+
+def launch_count() -> int:
+    return int(load().vsn_launch_count())
 
 
 def check_device() -> None:
@@ -77,8 +83,25 @@ def check_device() -> None:
         _device_checked = True
 
 
+# Optional per-call device timing (bench.py / profiling only): when PROFILE is a list, every call is
+# bracketed by CUDA events on the current stream and (name, tag, start, end) is appended.
+PROFILE = None
+TAG = ""
+WORK = (0, 0)   # (algorithmic flops, algorithmic bytes) of the next call, set by ops.py when profiling
+
+
 def call(name: str, *args) -> None:
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if PROFILE is None:
+        rc = getattr(lib, name)(*args)
+    else:
+        import torch
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = getattr(lib, name)(*args)
+        e.record()
+        global WORK
+        PROFILE.append((name, TAG, WORK, s, e))
+        WORK = (0, 0)
     if rc != 0:
         raise RuntimeError(f"{name} failed (code {rc}): {last_error()}")

@@ -23,6 +23,12 @@ int vsn_num_sms() {
   return sms;
 }
 
+// Number of kernel launches issued by this library since load (all threads); bench.py reports the
+// difference over its timed region as "gpu_launches".
+static unsigned long long g_launches = 0;
+void vsn_count_launch() { __atomic_add_fetch(&g_launches, 1ULL, __ATOMIC_RELAXED); }
+extern "C" long long vsn_launch_count() { return static_cast<long long>(__atomic_load_n(&g_launches, __ATOMIC_RELAXED)); }
+
 extern "C" const char* vsn_last_error() { return g_err; }
 
 extern "C" int vsn_version() { return 100; }

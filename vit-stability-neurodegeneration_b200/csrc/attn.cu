@@ -740,6 +740,7 @@ extern "C" int vsn_attn_bwd(const void* qkv, const void* out, const void* dout, 
     const size_t sq = 6 * Smem<HD>::TILE + extra_bytes<HD>(p, WIN, true);           \
     if (int rc = set_smem(attn_bwd_dq_kernel<HD, WIN>, sq)) return rc;              \
     attn_bwd_dq_kernel<HD, WIN><<<gq, 128, sq, st>>>(p);                            \
+    VSN_LAUNCH_CHECK();                                                             \
     const size_t sk = 6 * Smem<HD>::TILE + 4 * TQ * 4 + extra_bytes<HD>(p, WIN, false); \
     if (int rc = set_smem(attn_bwd_dkv_kernel<HD, WIN>, sk)) return rc;             \
     attn_bwd_dkv_kernel<HD, WIN><<<gk, 128, sk, st>>>(p);                           \

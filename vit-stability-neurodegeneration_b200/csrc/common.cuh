@@ -26,8 +26,10 @@ void vsn_set_error(const char* fmt, ...);
       return 2;                                                                          \
     }                                                                                    \
   } while (0)
+void vsn_count_launch();
 #define VSN_LAUNCH_CHECK()                                                               \
   do {                                                                                   \
+    vsn_count_launch();                                                                  \
     cudaError_t e__ = cudaGetLastError();                                                \
     if (e__ != cudaSuccess) {                                                            \
       vsn_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \

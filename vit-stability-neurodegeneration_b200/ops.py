@@ -36,6 +36,10 @@ def _require_cuda(*ts):
 def gemm(a, lda, a_mn, b, ldb, b_mn, M, N, K, out, ldo, out_kind, *, bias=None, act=0, aux=None, ldaux=0,
          resid=None, ldr=0, row_scale=None, rows_per_group=1, alpha=1.0, split_k=1):
     _require_cuda(a, b, out)
+    if _lib.PROFILE is not None:
+        _lib.TAG = f"M{M} N{N} K{K} majors={int(a_mn)}{int(b_mn)} out={out_kind} act={act}"
+        _lib.WORK = (2 * M * N * K, 2 * (M * K + N * K) + M * N * (2 if out_kind == 0 else 4)
+                     + (M * N * 4 if resid is not None else 0) + (M * N * 2 if act else 0))
     _lib.call("vsn_gemm_bf16", _p(a), lda, int(a_mn), _p(b), ldb, int(b_mn), M, N, K, _p(out), ldo, out_kind,
               _p(bias), act, _p(aux), ldaux, _p(resid), ldr, _p(row_scale), rows_per_group, float(alpha), split_k,
               _stream())
@@ -92,6 +96,9 @@ def layernorm_fwd(x: torch.Tensor, gamma, beta, *, out_dtype=BF16, eps: float = 
     y = torch.empty((rows, C), device=x.device, dtype=out_dtype)
     mean = torch.empty((rows,), device=x.device, dtype=F32) if want_stats else None
     rstd = torch.empty((rows,), device=x.device, dtype=F32) if want_stats else None
+    if _lib.PROFILE is not None:
+        _lib.TAG = f"rows{rows} C{C} out={'bf16' if out_dtype == BF16 else 'f32'}"
+        _lib.WORK = (0, rows * C * (4 + (2 if out_dtype == BF16 else 4)))
     _lib.call("vsn_layernorm_fwd", _p(x), x.stride(0), _p(gamma), _p(beta), _p(y), y.stride(0),
               1 if out_dtype == BF16 else 0, _p(mean), _p(rstd), rows, C, eps, _stream())
     return y, mean, rstd
@@ -104,6 +111,10 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, mean, rstd, gamma, *, resid
     _require_cuda(dy, x)
     dx = dx_out if dx_out is not None else (torch.empty((rows, C), device=x.device, dtype=F32) if want_dx else None)
     dxb = torch.empty((rows, C), device=x.device, dtype=BF16) if want_bf16 else None
+    if _lib.PROFILE is not None:
+        _lib.TAG = f"rows{rows} C{C} dy={'bf16' if dy.dtype == BF16 else 'f32'} dx={int(dx is not None)} dxb={int(dxb is not None)}"
+        _lib.WORK = (0, rows * C * ((2 if dy.dtype == BF16 else 4) + 4 + (4 if resid_grad is not None else 0)
+                                    + (4 if dx is not None else 0) + (2 if dxb is not None else 0)))
     _lib.call("vsn_layernorm_bwd", _p(dy), dy.stride(0), 1 if dy.dtype == BF16 else 0, _p(x), x.stride(0),
               _p(mean), _p(rstd), _p(gamma), _p(resid_grad), resid_grad.stride(0) if resid_grad is not None else 0,
               _p(dx), dx.stride(0) if dx is not None else 0, _p(dxb), C, _p(row_scale), rows_per_group, rows, C,
@@ -113,6 +124,9 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, mean, rstd, gamma, *, resid
 
 def ln_param_grad(dy, x, mean, rstd, dgamma, dbeta) -> None:
     rows, C = x.shape
+    if _lib.PROFILE is not None:
+        _lib.TAG = f"rows{rows} C{C} ln dy={'bf16' if dy.dtype == BF16 else 'f32'}"
+        _lib.WORK = (0, rows * C * ((2 if dy.dtype == BF16 else 4) + 4))
     _lib.call("vsn_colreduce", _p(dy), dy.stride(0), 1 if dy.dtype == BF16 else 0, _p(x), x.stride(0), _p(mean),
               _p(rstd), _p(dgamma), _p(dbeta), rows, C, _stream())
 
@@ -120,6 +134,9 @@ def ln_param_grad(dy, x, mean, rstd, dgamma, dbeta) -> None:
 def colsum(dy: torch.Tensor, out: torch.Tensor) -> None:
     """out[c] += sum_r dy[r, c]."""
     rows, C = dy.shape
+    if _lib.PROFILE is not None:
+        _lib.TAG = f"rows{rows} C{C} colsum"
+        _lib.WORK = (0, rows * C * (2 if dy.dtype == BF16 else 4))
     _lib.call("vsn_colreduce", _p(dy), dy.stride(0), 1 if dy.dtype == BF16 else 0, None, 0, None, None, None,
               _p(out), rows, C, _stream())
 
@@ -151,6 +168,9 @@ def attn_fwd(qkv: torch.Tensor, heads: int, hd: int, *, S: int, N: int, scale: f
     out = torch.empty((T, C), device=qkv.device, dtype=BF16)
     npad = (N + 63) // 64 * 64
     lse = torch.empty((S, heads, npad), device=qkv.device, dtype=F32) if want_lse else None
+    if _lib.PROFILE is not None:
+        _lib.TAG = f"S{S} N{N} heads{heads} hd{hd} win={int(geom is not None)} mask={int(bool(geom and geom.use_mask))}"
+        _lib.WORK = (4 * S * N * N * C, S * N * C * 2 * 4)
     _lib.call("vsn_attn_fwd", _p(qkv), _p(out), _p(lse), S, N, heads, hd, 1 if geom is not None else 0,
               ctypes.cast(geom.arr, ctypes.c_void_p) if geom is not None else None, _p(table),
               table.shape[0] if table is not None else 0, float(scale), _stream())
@@ -168,6 +188,9 @@ def attn_bwd(qkv, out, dout, lse, heads: int, hd: int, *, S: int, N: int, scale:
     dense = torch.zeros((heads, npad, npad), device=qkv.device, dtype=F32) if table is not None else None
     # real tokens are all written by the kernels; padded-grid tokens always belong to a window too
     dqkv = torch.empty_like(qkv)
+    if _lib.PROFILE is not None:
+        _lib.TAG = f"S{S} N{N} heads{heads} hd{hd} win={int(geom is not None)} mask={int(bool(geom and geom.use_mask))}"
+        _lib.WORK = (8 * S * N * N * heads * hd, S * N * heads * hd * 2 * 8)
     _lib.call("vsn_attn_bwd", _p(qkv), _p(out), _p(dout), _p(lse), _p(delta), _p(dqkv), _p(dense), _p(dtable), S, N,
               heads, hd, 1 if geom is not None else 0,
               ctypes.cast(geom.arr, ctypes.c_void_p) if geom is not None else None, _p(table),
@@ -216,6 +239,9 @@ def cast_rows_bf16(src: torch.Tensor, row_scale=None, rows_per_group=1) -> torch
     rows, C = src.shape
     assert src.dtype == F32 and src.is_contiguous()
     dst = torch.empty((rows, C), device=src.device, dtype=BF16)
+    if _lib.PROFILE is not None:
+        _lib.TAG = f"rows{rows} C{C}"
+        _lib.WORK = (0, rows * C * 6)
     _lib.call("vsn_cast_rows_bf16", _p(src), _p(dst), _p(row_scale), rows_per_group, rows, C, _stream())
     return dst
 
