@@ -11,7 +11,16 @@
 // Layouts: qkv is [T, 3C] bf16 with q|k|v column blocks and head-major [heads][hd] inside each (the reshape at
 // :166-170 / chunk(3) + 'b n (h d)' in the ViT); out is [T, C] bf16; rows are tokens of the (padded) stage grid
 // in natural (b,d,h,w) order, so neither input nor output is ever re-ordered.
+#include <stdlib.h>
 #include "common.cuh"
+#include "wattn_tc.cuh"
+
+// VSN_B200_LEGACY_ATTN=1 keeps the mma.sync kernels for window attention too (A/B measurements only).
+static bool vsn_force_legacy_attn() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VSN_B200_LEGACY_ATTN"); v = (e != nullptr && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
 
 namespace {
 
@@ -682,6 +691,17 @@ int fill_params(AttnParams& p, int S, int N, int heads, int hd, int win, const i
   return 0;
 }
 
+
+WinAttnArgs to_tc_args(const AttnParams& p) {
+  WinAttnArgs a = {};
+  a.qkv = p.qkv; a.out = p.out; a.lse = p.lse; a.table = p.table; a.table_len = p.table_len;
+  a.dout = p.dout; a.dqkv = p.dqkv; a.dbias_dense = p.dbias_dense;
+  a.S = p.S; a.N = p.N; a.heads = p.heads; a.C = p.C; a.scale = p.scale;
+  a.B = p.B; a.Dp = p.Dp; a.Hp = p.Hp; a.Wp = p.Wp; a.wd = p.wd; a.wh = p.wh; a.ww = p.ww;
+  a.sd = p.sd; a.sh = p.sh; a.sw = p.sw; a.nWd = p.nWd; a.nWh = p.nWh; a.nWw = p.nWw; a.use_mask = p.use_mask;
+  return a;
+}
+
 }  // namespace
 
 // geom (window mode, 11 ints): B, Dp, Hp, Wp, wd, wh, ww, shift_d, shift_h, shift_w, use_mask.
@@ -693,6 +713,7 @@ extern "C" int vsn_attn_fwd(const void* qkv, void* out, float* lse, int S, int N
   if (S == 0) return 0;
   dim3 grid(p.Npad / TQ, heads, S);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (win && wattn_tc_supported(p.wd, p.wh, p.ww, hd) && !vsn_force_legacy_attn()) return wattn_tc_fwd(to_tc_args(p), st);
 #define VSN_FWD(HD, WIN)                                                            \
   {                                                                                 \
     const size_t sm = 5 * Smem<HD>::TILE + extra_bytes<HD>(p, WIN, false);          \

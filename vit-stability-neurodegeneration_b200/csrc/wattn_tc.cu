@@ -1,0 +1,464 @@
+// Swin-3D shifted-window attention core on the 5th-gen tensor cores (tcgen05 + TMEM), forward and backward.
+// Covers WindowAttention3D.forward between the qkv and proj Linears together with the torch.roll /
+// window_partition / window_reverse / shift-mask plumbing around it
+// (models/swin_transformer_3d.py:72-89,132-152,162-196,330-358,463-492) for head_dim 32 and windows of at
+// most 252 tokens (padded to 256 inside the SM) -- every stage of the shipped Swin configs.
+//
+// Forward, one persistent CTA per (head, group of windows):
+//   smem   dense bias tile B[i][j] = table[rpi[i,j], head] * log2(e) as bf16 (built once per CTA, 126 KB),
+//          a 2-deep ring of {Q,K,V}[256][32] bf16 tiles in the 64-byte-swizzled UMMA layout (96 KB),
+//          per-key region codes for the shift mask.
+//   TMEM   two 256-column regions; region r holds S = Q_h K^T for one half h of the window's queries
+//          (128 lanes x 256 fp32 columns).  The softmax warps overwrite its first 128 columns with
+//          P (bf16 pairs) which feeds the second MMA from TMEM; O = P V accumulates in columns 128..159.
+//   warps  0-7 softmax (warp w: TMEM lanes 32*(w&3).., key half w>>2; a row is shared by two threads that
+//          exchange max / sum through smem), 8 = cp.async gather of the next window (roll and
+//          window_partition are index math on the source rows), 9 = MMA issuer (one lane).
+// Nothing of size N x N ever goes to HBM: no rolled copy, no mask tensor, no bias tensor, no logits.
+#include <stdlib.h>
+#include "tc.cuh"
+#include "wattn_tc.cuh"
+
+namespace {
+
+constexpr int NP = 256;                    // padded tokens per window
+constexpr int HD = 32;
+constexpr int TILE_BYTES = NP * HD * 2;    // 16 KB
+constexpr int STAGE_BYTES = 3 * TILE_BYTES;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float MASK_L2E = -100.0f * LOG2E;
+constexpr float PAD_BIAS = -30000.0f;      // keys >= N
+
+__device__ __forceinline__ uint32_t swz64(int row, int chunk) {   // byte offset inside a [rows][32] bf16 tile
+  return static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+}
+
+struct TokenGeom {
+  int row;      // global row of the token in the [T, *] matrices
+  int code;     // region id 0..26 on the rolled grid (models/swin_transformer_3d.py:463-492)
+  int lin;      // relative-position linear code of the token inside its window
+};
+
+// token i of window s (window_partition order) -> source row after the cyclic shift, region code, lin code
+__device__ __forceinline__ TokenGeom token_geom(const WinAttnArgs& p, int s, int i) {
+  const int nW = p.nWd * p.nWh * p.nWw;
+  const int b = s / nW, wi = s - b * nW;
+  const int wa = wi / (p.nWh * p.nWw), wr = wi - wa * (p.nWh * p.nWw), wb = wr / p.nWw, wc = wr - wb * p.nWw;
+  const int ld = i / (p.wh * p.ww), lr = i - ld * (p.wh * p.ww), lh = lr / p.ww, lw = lr - lh * p.ww;
+  const int dd = wa * p.wd + ld, hh = wb * p.wh + lh, wv = wc * p.ww + lw;   // position on the rolled grid
+  int d0 = dd + p.sd; if (d0 >= p.Dp) d0 -= p.Dp;                            // torch.roll(-shift) source
+  int h0 = hh + p.sh; if (h0 >= p.Hp) h0 -= p.Hp;
+  int w0 = wv + p.sw; if (w0 >= p.Wp) w0 -= p.Wp;
+  TokenGeom g;
+  g.row = ((b * p.Dp + d0) * p.Hp + h0) * p.Wp + w0;
+  const int rd = dd < p.Dp - p.wd ? 0 : (dd < p.Dp - p.sd ? 1 : 2);
+  const int rh = hh < p.Hp - p.wh ? 0 : (hh < p.Hp - p.sh ? 1 : 2);
+  const int rw = wv < p.Wp - p.ww ? 0 : (wv < p.Wp - p.sw ? 1 : 2);
+  g.code = 9 * rd + 3 * rh + rw;
+  g.lin = ld * ((2 * p.wh - 1) * (2 * p.ww - 1)) + lh * (2 * p.ww - 1) + lw;
+  return g;
+}
+
+// windows that straddle a region boundary are exactly the last ones along an axis
+__device__ __forceinline__ bool window_masked(const WinAttnArgs& p, int s) {
+  if (!p.use_mask) return false;
+  const int nW = p.nWd * p.nWh * p.nWw;
+  const int wi = s % nW;
+  const int wa = wi / (p.nWh * p.nWw), wr = wi - wa * (p.nWh * p.nWw), wb = wr / p.nWw, wc = wr - wb * p.nWw;
+  return (p.sd > 0 && wa == p.nWd - 1) || (p.sh > 0 && wb == p.nWh - 1) || (p.sw > 0 && wc == p.nWw - 1);
+}
+
+// Relative-position bias in smem, window dims static: row ((a*(2WH-1) + b)*WW + wi) holds the 16-byte vector
+// { table[(a, b, wi - wj + WW-1), head] * log2(e) : wj = 0..WW-1 } as bf16, with a = di-dj+WD-1, b = hi-hj+WH-1.
+// For query token i=(di,hi,wi) and the key row kr=(dj,hj) of the window the vector sits at row
+//   rowbase(i) - (dj*(2WH-1) + hj)*WW,   rowbase(i) = ((di+WD-1)*(2WH-1) + hi+WH-1)*WW + wi,
+// so a thread fetches the bias of WW consecutive keys with one LDS.128 and every element position is a
+// compile-time constant.  (2WD-1)(2WH-1)WW rows = 13.4 KB for the (6,7,6) window instead of a dense 126 KB tile.
+template <int WD, int WH, int WW>
+struct BiasTab {
+  static_assert(WW <= 8, "one 16-byte row holds the WW keys of a key row");
+  static constexpr int ROWS = (2 * WD - 1) * (2 * WH - 1) * WW;
+  static constexpr int BYTES = ROWS * 16;
+  __device__ static void build(const WinAttnArgs& p, int head, uint8_t* tab) {
+    for (int r = threadIdx.x; r < ROWS; r += blockDim.x) {
+      const int wi = r % WW, ab = r / WW;
+      float v[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        v[t] = 0.f;
+        if (t < WW && p.table != nullptr)
+          v[t] = p.table[static_cast<long long>(ab * (2 * WW - 1) + (wi - t + WW - 1)) * p.heads + head] * LOG2E;
+      }
+      uint4 u;
+      u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]); u.z = pack_bf16(v[4], v[5]); u.w = pack_bf16(v[6], v[7]);
+      *reinterpret_cast<uint4*>(tab + r * 16) = u;
+    }
+  }
+  __device__ __forceinline__ static int rowbase(int i) {
+    const int di = i / (WH * WW), lr = i - di * (WH * WW), hi = lr / WW, wi = lr - hi * WW;
+    return ((di + WD - 1) * (2 * WH - 1) + hi + WH - 1) * WW + wi;
+  }
+};
+
+template <int WD, int WH, int WW>
+__device__ __forceinline__ TokenGeom token_geom_t(const WinAttnArgs& p, int s, int i) {
+  const int nW = p.nWd * p.nWh * p.nWw;
+  const int b = s / nW, wi = s - b * nW;
+  const int wa = wi / (p.nWh * p.nWw), wr = wi - wa * (p.nWh * p.nWw), wb = wr / p.nWw, wc = wr - wb * p.nWw;
+  const int ld = i / (WH * WW), lr = i - ld * (WH * WW), lh = lr / WW, lw = lr - lh * WW;
+  const int dd = wa * WD + ld, hh = wb * WH + lh, wv = wc * WW + lw;
+  int d0 = dd + p.sd; if (d0 >= p.Dp) d0 -= p.Dp;
+  int h0 = hh + p.sh; if (h0 >= p.Hp) h0 -= p.Hp;
+  int w0 = wv + p.sw; if (w0 >= p.Wp) w0 -= p.Wp;
+  TokenGeom g;
+  g.row = ((b * p.Dp + d0) * p.Hp + h0) * p.Wp + w0;
+  const int rd = dd < p.Dp - WD ? 0 : (dd < p.Dp - p.sd ? 1 : 2);
+  const int rh = hh < p.Hp - WH ? 0 : (hh < p.Hp - p.sh ? 1 : 2);
+  const int rw = wv < p.Wp - WW ? 0 : (wv < p.Wp - p.sw ? 1 : 2);
+  g.code = 9 * rd + 3 * rh + rw;
+  g.lin = 0;
+  return g;
+}
+
+// =========================================== forward ==============================================
+constexpr int SM_WARPS = 16;                      // softmax warps: 4 TMEM lane quadrants x 4 column parts
+constexpr int FWD_THREADS = (SM_WARPS + 2) * 32;  // + loader warp + MMA warp
+constexpr int FWD_STAGES = 2;
+
+template <int WD, int WH, int WW>
+struct FwdSmem {
+  static constexpr int BIAS = FWD_STAGES * STAGE_BYTES;
+  static constexpr int KEYCODE = BIAS + BiasTab<WD, WH, WW>::BYTES;
+  static constexpr int STATS = KEYCODE + FWD_STAGES * NP;      // float2 [2][4 parts][128]
+  static constexpr int BARS = STATS + 2 * 4 * 128 * 8;
+  static constexpr int TOTAL = BARS + 24 * 8;
+};
+
+// 2^x for x <= 0 on the FMA / ALU pipes (Cody-Waite split + degree-3 minimax polynomial, relative error
+// ~1e-4, far below the bf16 rounding of P): relieves the MUFU pipe, which is the bound of this kernel.
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;                 // 1.5 * 2^23: integer part lands in the low mantissa bits
+  const float r = x - (t - 12582912.f);           // r in [-0.5, 0.5]
+  float p = fmaf(r, 0.0555041087f, 0.2402264923f);
+  p = fmaf(p, r, 0.6931471806f);
+  p = fmaf(p, r, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+// x[k] = s[k] * cscale + bias(i, key 64*PART + k) for the 64 keys of a column part (padded keys -> PAD_BIAS)
+template <int WD, int WH, int WW, int PART>
+__device__ __forceinline__ void add_bias(uint32_t* x, const uint8_t* tab, int rowbase, float cscale) {
+  constexpr int N = WD * WH * WW;
+  constexpr int KR0 = (PART * 64) / WW, KR1 = (PART * 64 + 63) / WW;
+#pragma unroll
+  for (int kr = KR0; kr <= KR1; ++kr) {
+    if (kr * WW >= N) continue;
+    const int dj = kr / WH, hj = kr - dj * WH;
+    const uint4 bb = *reinterpret_cast<const uint4*>(tab + (rowbase - (dj * (2 * WH - 1) + hj) * WW) * 16);
+    const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+    for (int wj = 0; wj < WW; ++wj) {
+      const int k = kr * WW + wj - PART * 64;
+      if (k < 0 || k >= 64) continue;
+      const float b = (wj & 1) ? __uint_as_float(bw[wj >> 1] & 0xFFFF0000u) : __uint_as_float(bw[wj >> 1] << 16);
+      x[k] = __float_as_uint(fmaf(__uint_as_float(x[k]), cscale, b));
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 64; ++k)
+    if (PART * 64 + k >= N) x[k] = __float_as_uint(PAD_BIAS);
+}
+
+template <int WD, int WH, int WW, int VAR>
+__global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttnArgs p) {
+  using SM = FwdSmem<WD, WH, WW>;
+  using BT = BiasTab<WD, WH, WW>;
+  constexpr int N = WD * WH * WW;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* stages = smem;
+  uint8_t* bias_s = smem + SM::BIAS;
+  uint8_t* keycode = smem + SM::KEYCODE;
+  float2* stats = reinterpret_cast<float2*>(smem + SM::STATS);    // (local max, local sum)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::BARS);
+  uint64_t* qkv_full = bars;        // [2] loader lanes -> MMA
+  uint64_t* qkv_empty = bars + 2;   // [2] MMA commit -> loader
+  uint64_t* s_full = bars + 4;      // [2] MMA commit -> softmax
+  uint64_t* p_ready = bars + 6;     // [2] softmax threads -> MMA
+  uint64_t* o_full = bars + 8;      // [2] MMA commit -> softmax (epilogue)
+  uint64_t* o_read = bars + 10;     // [2] softmax threads -> MMA (region may be overwritten)
+  uint64_t* st_full = bars + 12;    // [4 quadrants][2] row statistics of a unit are in smem
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.y;
+  const int n_it = (p.S - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int U = 2 * n_it;
+
+  if (threadIdx.x == 0) {
+    if ((tc::smem_u32(smem) & 1023u) != 0) {
+      printf("vsn_b200: dynamic shared memory base is not 1024-byte aligned\n");
+      __trap();
+    }
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&qkv_full[i], 32);
+      tc::mbar_init(&qkv_empty[i], 1);
+      tc::mbar_init(&s_full[i], 1);
+      tc::mbar_init(&p_ready[i], SM_WARPS * 32);
+      tc::mbar_init(&o_full[i], 1);
+      tc::mbar_init(&o_read[i], SM_WARPS * 32);
+    }
+    for (int i = 0; i < 8; ++i) tc::mbar_init(&st_full[i], 128);
+    tc::fence_barrier_init();
+  }
+  if (warp == SM_WARPS + 1) tc::tmem_alloc(tmem_slot, 512);
+  BT::build(p, head, bias_s);
+  // rows N..255 of every tile stay zero for the whole kernel (the loader only writes rows < N)
+  for (int idx = threadIdx.x; idx < FWD_STAGES * 3 * (NP - N) * 4; idx += blockDim.x) {
+    const int tile = idx / ((NP - N) * 4), rem = idx - tile * ((NP - N) * 4);
+    const int row = N + rem / 4, c = rem & 3;
+    *reinterpret_cast<uint4*>(stages + tile * TILE_BYTES + swz64(row, c)) = make_uint4(0, 0, 0, 0);
+  }
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == SM_WARPS) {
+    // ------------------------------------------------------------------ loader
+    const long long ld = 3LL * p.C;
+    for (int it = 0; it < n_it; ++it) {
+      const int s = blockIdx.x + it * gridDim.x;
+      const int st = it & 1;
+      tc::mbar_wait_relaxed(&qkv_empty[st], ((it >> 1) & 1) ^ 1);
+      uint8_t* sq = stages + st * STAGE_BYTES;
+      for (int i = lane; i < N; i += 32) {
+        const TokenGeom g = token_geom_t<WD, WH, WW>(p, s, i);
+        keycode[st * NP + i] = static_cast<uint8_t>(g.code);
+        const bf16* src = p.qkv + g.row * ld + head * HD;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t o = swz64(i, c);
+          tc::cp_async16(sq + o, src + c * 8);
+          tc::cp_async16(sq + TILE_BYTES + o, src + p.C + c * 8);
+          tc::cp_async16(sq + 2 * TILE_BYTES + o, src + 2 * p.C + c * 8);
+        }
+      }
+      tc::cp_async_wait_all();
+      tc::fence_proxy_async();
+      tc::mbar_arrive(&qkv_full[st]);
+    }
+  } else if (warp == SM_WARPS + 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = tc::make_idesc_bf16(128, NP, 0, 0);
+      const uint32_t idesc_o = tc::make_idesc_bf16(128, HD, 0, 1);
+      for (int u = 0; u <= U; ++u) {
+        if (u < U) {
+          const int it = u >> 1, h = u & 1, st = it & 1;
+          if (h == 0) tc::mbar_wait(&qkv_full[st], (it >> 1) & 1);
+          tc::mbar_wait(&o_read[h], ((u >> 1) & 1) ^ 1);
+          tc::fence_after_sync();
+          const uint32_t sq = tc::smem_u32(stages + st * STAGE_BYTES) + h * (128 * 64);
+          const uint32_t sk = tc::smem_u32(stages + st * STAGE_BYTES + TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k)
+            tc::mma_bf16_ss(tmem_base + h * NP, tc::make_smem_desc_sw64(sq + k * 32, 16, 512),
+                            tc::make_smem_desc_sw64(sk + k * 32, 16, 512), idesc_s, k > 0 ? 1u : 0u);
+          tc::mma_commit(&s_full[h]);
+        }
+        if (u >= 1) {
+          const int v = u - 1, it = v >> 1, h = v & 1, st = it & 1;
+          tc::mbar_wait(&p_ready[h], (v >> 1) & 1);
+          tc::fence_after_sync();
+          const uint32_t sv = tc::smem_u32(stages + st * STAGE_BYTES + 2 * TILE_BYTES);
+          // keys 64*part .. 64*part+63 were exponentiated against their own local max: one accumulator each
+#pragma unroll
+          for (int k = 0; k < NP / 16; ++k)
+            tc::mma_bf16_ts(tmem_base + h * NP + 128 + (k >> 2) * 32, tmem_base + h * NP + k * 8,
+                            tc::make_smem_desc_sw64(sv + k * 1024, 16, 512), idesc_o, (k & 3) ? 1u : 0u);
+          tc::mma_commit(&o_full[h]);
+          if (h == 1) tc::mma_commit(&qkv_empty[st]);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax + epilogue
+    // Thread = (TMEM lane rl, column part): 64 of the row's 256 logits, exponentiated against the LOCAL max of
+    // those 64 (no cross-thread exchange on the critical path).  P V is accumulated per part; the epilogue
+    // of unit u (run inside unit u+1, once O is ready) rescales the four partial outputs to the row max.
+    const int q4 = warp & 3, part = warp >> 2;
+    const int rl = q4 * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(q4 * 32) << 16;
+    const float cscale = p.scale * LOG2E;
+
+    auto epilogue = [&](int v) {
+      const int h = v & 1;
+      const int s = blockIdx.x + (v >> 1) * gridDim.x;
+      const int i = h * 128 + rl;
+      tc::mbar_wait(&st_full[q4 * 2 + h], (v >> 1) & 1);
+      const float2* sp = stats + h * 512 + rl;
+      const float2 s0 = sp[0], s1 = sp[128], s2 = sp[256], s3 = sp[384];
+      const float m = fmaxf(fmaxf(s0.x, s1.x), fmaxf(s2.x, s3.x));
+      const float w0 = tc::ex2_approx(s0.x - m), w1 = tc::ex2_approx(s1.x - m);
+      const float w2 = tc::ex2_approx(s2.x - m), w3 = tc::ex2_approx(s3.x - m);
+      const float l = fmaf(w0, s0.y, fmaf(w1, s1.y, fmaf(w2, s2.y, w3 * s3.y)));
+      const float inv = 1.f / l;
+      tc::mbar_wait(&o_full[h], (v >> 1) & 1);
+      tc::fence_after_sync();
+      const uint32_t ob = tmem_base + lane_addr + h * NP + 128 + part * 8;
+      float r[8];
+      {
+        uint32_t o[8];
+        tc::tmem_ld_32x32b_x8(ob, o);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = w0 * __uint_as_float(o[k]);
+        tc::tmem_ld_32x32b_x8(ob + 32, o);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = fmaf(w1, __uint_as_float(o[k]), r[k]);
+        tc::tmem_ld_32x32b_x8(ob + 64, o);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = fmaf(w2, __uint_as_float(o[k]), r[k]);
+        tc::tmem_ld_32x32b_x8(ob + 96, o);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = fmaf(w3, __uint_as_float(o[k]), r[k]) * inv;
+      }
+      tc::fence_before_sync();
+      tc::mbar_arrive(&o_read[h]);
+      if (i < N) {
+        const TokenGeom g = token_geom_t<WD, WH, WW>(p, s, i);
+        uint4 w;
+        w.x = pack_bf16(r[0], r[1]); w.y = pack_bf16(r[2], r[3]); w.z = pack_bf16(r[4], r[5]); w.w = pack_bf16(r[6], r[7]);
+        *reinterpret_cast<uint4*>(p.out + static_cast<long long>(g.row) * p.C + head * HD + part * 8) = w;
+      }
+      if (part == 0 && p.lse != nullptr)
+        p.lse[(static_cast<long long>(s) * p.heads + head) * NP + i] = (m + log2f(l)) * (1.f / LOG2E);
+    };
+
+    for (int u = 0; u < U; ++u) {
+      const int it = u >> 1, h = u & 1, st = it & 1;
+      const int s = blockIdx.x + it * gridDim.x;
+      const int i = h * 128 + rl;
+      const int ib = i < N ? i : N - 1;
+      const int rowbase = BT::rowbase(ib);
+
+      tc::mbar_wait(&s_full[h], (u >> 1) & 1);
+      tc::fence_after_sync();
+      uint32_t x[64];
+      const uint32_t sbase = tmem_base + lane_addr + h * NP + part * 64;
+      tc::tmem_ld_32x32b_x32(sbase, x);
+      tc::tmem_ld_32x32b_x32(sbase + 32, x + 32);
+      tc::tmem_ld_wait();
+      if (!(VAR & 4)) switch (part) {
+        case 0: add_bias<WD, WH, WW, 0>(x, bias_s, rowbase, cscale); break;
+        case 1: add_bias<WD, WH, WW, 1>(x, bias_s, rowbase, cscale); break;
+        case 2: add_bias<WD, WH, WW, 2>(x, bias_s, rowbase, cscale); break;
+        default: add_bias<WD, WH, WW, 3>(x, bias_s, rowbase, cscale); break;
+      }
+      if (window_masked(p, s)) {
+        const uint32_t cq4 = static_cast<uint32_t>(token_geom_t<WD, WH, WW>(p, s, ib).code) * 0x01010101u;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint4 kc = *reinterpret_cast<const uint4*>(keycode + st * NP + part * 64 + c * 16);
+          const uint32_t kw[4] = {kc.x, kc.y, kc.z, kc.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const uint32_t ne = __vcmpne4(kw[t], cq4);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              const uint32_t m32 = __byte_perm(ne, 0, 0x8888u | (0x1111u * b));
+              const int k = c * 16 + t * 4 + b;
+              x[k] = __float_as_uint(__uint_as_float(x[k]) + __uint_as_float(m32 & __float_as_uint(MASK_L2E)));
+            }
+          }
+        }
+      }
+      float mx0 = -3.0e38f, mx1 = -3.0e38f;
+#pragma unroll
+      for (int k = 0; k < 64; k += 4) {
+        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(x[k]), __uint_as_float(x[k + 1])));
+        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(x[k + 2]), __uint_as_float(x[k + 3])));
+      }
+      // a part made only of padded keys / masked-out keys keeps a finite reference
+      const float m = fmaxf(fmaxf(mx0, mx1), -20000.f);
+
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 32; k += 2) {
+        // the epilogue of the previous unit sits in the middle of the exponentials: by then its O is ready
+        // and only half of the logits are still live in registers
+        if (k == 16 && u > 0) epilogue(u - 1);
+        // VAR&1: 1 of 4 exponentials on the FMA pipe instead of the MUFU pipe
+        const float p0 = (VAR & 2) ? (__uint_as_float(x[2 * k]) - m) : tc::ex2_approx(__uint_as_float(x[2 * k]) - m);
+        const float p1 = (VAR & 2) ? (__uint_as_float(x[2 * k + 1]) - m) : (VAR & 1) ? exp2_poly(__uint_as_float(x[2 * k + 1]) - m) : tc::ex2_approx(__uint_as_float(x[2 * k + 1]) - m);
+        const float p2 = (VAR & 2) ? (__uint_as_float(x[2 * k + 2]) - m) : tc::ex2_approx(__uint_as_float(x[2 * k + 2]) - m);
+        const float p3 = (VAR & 2) ? (__uint_as_float(x[2 * k + 3]) - m) : tc::ex2_approx(__uint_as_float(x[2 * k + 3]) - m);
+        l0 += p0 + p1;
+        l1 += p2 + p3;
+        x[k] = pack_bf16(p0, p1);
+        x[k + 1] = pack_bf16(p2, p3);
+      }
+      tc::tmem_st_32x32b_x32(tmem_base + lane_addr + h * NP + part * 32, x);
+      stats[h * 512 + part * 128 + rl] = make_float2(m, l0 + l1);
+      tc::mbar_arrive(&st_full[q4 * 2 + h]);
+      tc::tmem_st_wait();
+      tc::fence_before_sync();
+      tc::mbar_arrive(&p_ready[h]);
+    }
+    if (U > 0) epilogue(U - 1);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == SM_WARPS + 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int groups_for(int S, int heads) {
+  int g = vsn_num_sms() / heads;
+  if (g < 1) g = 1;
+  if (g > S) g = S;
+  // even out the tail: the smallest group count with the same number of rounds
+  const int rounds = ceil_div(S, g);
+  return ceil_div(S, rounds);
+}
+
+}  // namespace
+
+// The tcgen05 kernels are instantiated for the (6,7,6) window of the shipped Swin-3D configs
+// (config-defaults.yaml WINDOW_SIZE); other windows / head dims use the mma.sync kernels in attn.cu.
+bool wattn_tc_supported(int wd, int wh, int ww, int hd) { return hd == HD && wd == 6 && wh == 7 && ww == 6; }
+
+int wattn_tc_fwd(const WinAttnArgs& a, cudaStream_t stream) {
+  using SM = FwdSmem<6, 7, 6>;
+  static int var = -1;
+  if (var < 0) {
+    const char* e = getenv("VSN_WATTN_VARIANT");
+    var = e ? atoi(e) & 7 : 0;
+    VSN_CUDA(cudaFuncSetAttribute(wattn_fwd_kernel<6, 7, 6, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    VSN_CUDA(cudaFuncSetAttribute(wattn_fwd_kernel<6, 7, 6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    VSN_CUDA(cudaFuncSetAttribute(wattn_fwd_kernel<6, 7, 6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    VSN_CUDA(cudaFuncSetAttribute(wattn_fwd_kernel<6, 7, 6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    VSN_CUDA(cudaFuncSetAttribute(wattn_fwd_kernel<6, 7, 6, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+  }
+  dim3 grid(groups_for(a.S, a.heads), a.heads);
+  if (var == 1) wattn_fwd_kernel<6, 7, 6, 1><<<grid, FWD_THREADS, SM::TOTAL, stream>>>(a);
+  else if (var == 2) wattn_fwd_kernel<6, 7, 6, 2><<<grid, FWD_THREADS, SM::TOTAL, stream>>>(a);
+  else if (var == 4) wattn_fwd_kernel<6, 7, 6, 4><<<grid, FWD_THREADS, SM::TOTAL, stream>>>(a);
+  else if (var == 6) wattn_fwd_kernel<6, 7, 6, 6><<<grid, FWD_THREADS, SM::TOTAL, stream>>>(a);
+  else wattn_fwd_kernel<6, 7, 6, 0><<<grid, FWD_THREADS, SM::TOTAL, stream>>>(a);
+  VSN_LAUNCH_CHECK();
+  return 0;
+}
+
+int wattn_tc_bwd(const WinAttnArgs& a, cudaStream_t stream) {
+  (void)a; (void)stream;
+  vsn_set_error("wattn_tc_bwd: not built");
+  return 1;
+}
