@@ -631,8 +631,9 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnParams p) {
 }
 
 // dtable[r, a] += sum over (i,j) with relative_position_index[i,j] == r of dense[a, i, j]
+// transposed = 1: dense is [heads][key j][query i] (tcgen05 path), else [heads][query i][key j].
 __global__ void bias_table_grad_kernel(const float* __restrict__ dense, float* __restrict__ dtable, int heads, int N,
-                                       int Npad, int wd, int wh, int ww, int table_len) {
+                                       int Npad, int wd, int wh, int ww, int table_len, int transposed) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= table_len * heads) return;
   const int a = idx % heads, r = idx / heads;
@@ -644,7 +645,8 @@ __global__ void bias_table_grad_kernel(const float* __restrict__ dense, float* _
     const int jd = id - dd, jh = ih - dh, jw = iw - dw;
     if (jd < 0 || jd >= wd || jh < 0 || jh >= wh || jw < 0 || jw >= ww) continue;
     const int j = (jd * wh + jh) * ww + jw;
-    acc += dense[(static_cast<long long>(a) * Npad + i) * Npad + j];
+    acc += transposed ? dense[(static_cast<long long>(a) * Npad + j) * Npad + i]
+                      : dense[(static_cast<long long>(a) * Npad + i) * Npad + j];
   }
   dtable[static_cast<long long>(r) * heads + a] += acc;
 }
@@ -743,6 +745,16 @@ extern "C" int vsn_attn_bwd(const void* qkv, const void* out, const void* dout, 
   if (S == 0) return 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bf16* o = reinterpret_cast<const bf16*>(out);
+  if (win && wattn_tc_supported(p.wd, p.wh, p.ww, hd) && !vsn_force_legacy_attn()) {
+    p.out = const_cast<bf16*>(o);
+    if (int rc = wattn_tc_bwd(to_tc_args(p), delta, st)) return rc;
+    if (table != nullptr) {
+      const int n = table_len * heads;
+      bias_table_grad_kernel<<<ceil_div(n, 128), 128, 0, st>>>(dbias_dense, dtable, heads, N, p.Npad, p.wd, p.wh, p.ww, table_len, 1);
+      VSN_LAUNCH_CHECK();
+    }
+    return 0;
+  }
   if (win) attn_delta_kernel<true><<<S, 128, 0, st>>>(p, o, delta);
   else attn_delta_kernel<false><<<S, 128, 0, st>>>(p, o, delta);
   VSN_LAUNCH_CHECK();
@@ -774,7 +786,7 @@ extern "C" int vsn_attn_bwd(const void* qkv, const void* out, const void* dout, 
   VSN_LAUNCH_CHECK();
   if (table != nullptr) {
     const int n = table_len * heads;
-    bias_table_grad_kernel<<<ceil_div(n, 128), 128, 0, st>>>(dbias_dense, dtable, heads, N, p.Npad, p.wd, p.wh, p.ww, table_len);
+    bias_table_grad_kernel<<<ceil_div(n, 128), 128, 0, st>>>(dbias_dense, dtable, heads, N, p.Npad, p.wd, p.wh, p.ww, table_len, 0);
     VSN_LAUNCH_CHECK();
   }
   return 0;

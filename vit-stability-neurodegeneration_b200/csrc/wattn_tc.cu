@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
         *reinterpret_cast<uint4*>(p.out + static_cast<long long>(g.row) * p.C + head * HD + part * 8) = w;
       }
       if (part == 0 && p.lse != nullptr)
-        p.lse[(static_cast<long long>(s) * p.heads + head) * NP + i] = (m + log2f(l)) * (1.f / LOG2E);
+        p.lse[(static_cast<long long>(s) * p.heads + head) * NP + i] = m + log2f(l);   // log2 domain (consumed by wattn_bwd_kernel)
     };
 
     for (int u = 0; u < U; ++u) {
@@ -457,8 +457,429 @@ int wattn_tc_fwd(const WinAttnArgs& a, cudaStream_t stream) {
   return 0;
 }
 
-int wattn_tc_bwd(const WinAttnArgs& a, cudaStream_t stream) {
-  (void)a; (void)stream;
-  vsn_set_error("wattn_tc_bwd: not built");
-  return 1;
+// =========================================== backward =============================================
+// CTA = (head, half kh of the window's keys), persistent over a group of windows.  TMEM lanes are KEYS:
+//   S^T = K_half Q^T and dP^T = V_half dO^T are computed per sub-tile of 32 queries (two 64-column buffers),
+//   the compute threads turn them into P^T = exp2(S^T*c + B^T - lse) and dS^T = P^T (dP^T - delta) in place
+//   (bf16 pairs over their own columns), which feed straight from TMEM
+//     dV += P^T dO_sub,   dK += dS^T Q_sub,   dBias[:, sub] += dS^T I16   (identity B operand: the dense
+//     bias gradient of this (head, key half) accumulates over ALL windows of the CTA in 256 TMEM columns),
+//   while a copy of dS^T in an MN-major smem tile gives dQ_half = dS K_half (two 128-query blocks).
+//   dQ is the sum of the two key halves: bf16x2 red.add into the zeroed Q block of dqkv.
+// Warps: 0-7 compute group 0 (even sub-tiles), 8-15 group 1 (odd sub-tiles; also the per-window read-out of
+// dK / dV / dQ), 16 loader, 17 MMA issuer.  Thread = (key row, 16 of the sub-tile's 32 queries).
+constexpr int BWD_THREADS = 18 * 32;
+constexpr int QS = 32;                         // queries per sub-tile
+constexpr int NSUB = NP / QS;                  // 8
+constexpr int BWD_STAGE_BYTES = 51712;         // Q 16K | dO 16K | K_half 8K | V_half 8K | lse2 1K | delta 1K | qcode 256
+constexpr int DS_TILE_BYTES = 128 * NP * 2;    // 64 KB: dS^T as MN-major A operand, 128B swizzle
+
+template <int WD, int WH, int WW>
+struct BwdSmem {
+  static constexpr int DS = 2 * BWD_STAGE_BYTES;                    // 103424 (1024-aligned)
+  static constexpr int BIAS = DS + DS_TILE_BYTES;
+  static constexpr int IDENT = BIAS + ((BiasTab<WD, WH, WW>::BYTES + 1023) / 1024) * 1024;
+  static constexpr int BARS = IDENT + 1024;
+  static constexpr int TOTAL = BARS + 32 * 8;
+};
+
+// Transposed bias table: row ((a*(2WH-1)+b)*WW + wj) holds { table[(a, b, wi - wj + WW-1)] * log2e : wi = 0..WW-1 },
+// so a KEY thread fetches the bias against the WW queries of one query row with one LDS.128:
+//   row = rowbaseT(j) + (di*(2WH-1) + hi)*WW,  rowbaseT(j) = ((WD-1-dj)*(2WH-1) + WH-1-hj)*WW + wj.
+template <int WD, int WH, int WW>
+__device__ void build_bias_t(const WinAttnArgs& p, int head, uint8_t* tab) {
+  constexpr int ROWS = BiasTab<WD, WH, WW>::ROWS;
+  for (int r = threadIdx.x; r < ROWS; r += blockDim.x) {
+    const int wj = r % WW, ab = r / WW;
+    float v[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      v[t] = 0.f;
+      if (t < WW && p.table != nullptr)
+        v[t] = p.table[static_cast<long long>(ab * (2 * WW - 1) + (t - wj + WW - 1)) * p.heads + head] * LOG2E;
+    }
+    uint4 u;
+    u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]); u.z = pack_bf16(v[4], v[5]); u.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(tab + r * 16) = u;
+  }
+}
+
+// x[k] = s[k]*cscale + bias(query q0+k, my key) for 16 consecutive queries starting at q0 (q0 % 6 == W0)
+template <int WD, int WH, int WW, int W0>
+__device__ __forceinline__ void add_bias_t16(float* x, const uint8_t* tab, int rowbaseT, int qr0, float cscale) {
+  constexpr int NR = (W0 + 15) / WW + 1;
+  constexpr int QR_MAX = WD * WH - 1;
+  uint32_t bw[NR][4];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    int qr = qr0 + r;
+    qr = qr > QR_MAX ? QR_MAX : qr;                       // padded queries read a valid row (result unused)
+    const int di = qr / WH, hi = qr - di * WH;
+    const uint4 bb = *reinterpret_cast<const uint4*>(tab + (rowbaseT + (di * (2 * WH - 1) + hi) * WW) * 16);
+    bw[r][0] = bb.x; bw[r][1] = bb.y; bw[r][2] = bb.z; bw[r][3] = bb.w;
+  }
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int r = (W0 + k) / WW, wi = (W0 + k) % WW;
+    const float b = (wi & 1) ? __uint_as_float(bw[r][wi >> 1] & 0xFFFF0000u) : __uint_as_float(bw[r][wi >> 1] << 16);
+    x[k] = fmaf(x[k], cscale, b);
+  }
+}
+
+__device__ __forceinline__ void red_add_bf16x2(bf16* addr, uint32_t v) {
+  asm volatile("red.global.add.noftz.bf16x2 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+
+template <int WD, int WH, int WW>
+__global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttnArgs p, const float* __restrict__ delta_g) {
+  using SM = BwdSmem<WD, WH, WW>;
+  constexpr int N = WD * WH * WW;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* stages = smem;
+  uint8_t* ds_tile = smem + SM::DS;
+  uint8_t* bias_s = smem + SM::BIAS;
+  uint8_t* ident = smem + SM::IDENT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::BARS);
+  uint64_t* ld_full = bars;          // [2] loader lanes -> MMA
+  uint64_t* ld_empty = bars + 2;     // [2] MMA commit -> loader
+  uint64_t* s_full = bars + 4;       // [2 buffers] MMA commit -> compute group
+  uint64_t* p_ready = bars + 6;      // [2 buffers] compute group -> MMA
+  uint64_t* ds_free = bars + 8;      // [2 query blocks] MMA commit (dQ block done) -> compute threads (smem tile half)
+  uint64_t* unit_done = bars + 10;   // MMA commit: dK, dV, dQ of the window complete -> group 1
+  uint64_t* acc_read = bars + 11;    // group 1: accumulators read out -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.y, kh = blockIdx.z;
+  const int n_units = (p.S - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int TT = n_units * NSUB;     // sub-tiles of this CTA
+
+  // TMEM map (columns): [0,256) dBias accumulator | buffer b at 256+64b: S^T [0,32) dP^T [32,64) |
+  //                     384.. dQ (2 x 32) | 448.. dV | 480.. dK
+  constexpr uint32_t COL_BUF = 256, COL_DQ = 384, COL_DV = 448, COL_DK = 480;
+
+  if (threadIdx.x == 0) {
+    if ((tc::smem_u32(smem) & 1023u) != 0) {
+      printf("vsn_b200: dynamic shared memory base is not 1024-byte aligned\n");
+      __trap();
+    }
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&ld_full[i], 32);
+      tc::mbar_init(&ld_empty[i], 1);
+      tc::mbar_init(&s_full[i], 1);
+      tc::mbar_init(&p_ready[i], 256);
+      tc::mbar_init(&ds_free[i], 1);
+    }
+    tc::mbar_init(unit_done, 1);
+    tc::mbar_init(acc_read, 256);
+    tc::fence_barrier_init();
+  }
+  if (warp == 17) tc::tmem_alloc(tmem_slot, 512);
+  build_bias_t<WD, WH, WW>(p, head, bias_s);
+  // zero everything that the loader never writes: pad rows of the tiles, the identity tile, lse/delta pads
+  for (int i = threadIdx.x; i < 2 * BWD_STAGE_BYTES / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(stages)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(ident)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  if (threadIdx.x < 16)   // I16 as a K-major [16 rows][32] tile (64-byte swizzle), element (n, n) = 1
+    *reinterpret_cast<bf16*>(ident + swz64(threadIdx.x, threadIdx.x >> 3) + (threadIdx.x & 7) * 2) = __float2bfloat16(1.0f);
+  for (int i = threadIdx.x; i < 2 * (NP - N); i += blockDim.x) {
+    const int st = i / (NP - N), q = N + i % (NP - N);
+    reinterpret_cast<float*>(stages + st * BWD_STAGE_BYTES + 49152)[q] = 30000.f;   // lse2 pad -> P = 0
+  }
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 16) {
+    // ------------------------------------------------------------------ loader
+    const long long ld = 3LL * p.C;
+    for (int n = 0; n < n_units; ++n) {
+      const int s = blockIdx.x + n * gridDim.x;
+      const int st = n & 1;
+      tc::mbar_wait_relaxed(&ld_empty[st], ((n >> 1) & 1) ^ 1);
+      uint8_t* sb = stages + st * BWD_STAGE_BYTES;
+      for (int i = lane; i < N; i += 32) {
+        const TokenGeom g = token_geom_t<WD, WH, WW>(p, s, i);
+        sb[51200 + i] = static_cast<uint8_t>(g.code);
+        const bf16* src = p.qkv + g.row * ld + head * HD;
+        const bf16* dsrc = p.dout + static_cast<long long>(g.row) * p.C + head * HD;
+        const int kr = i - kh * 128;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t o = swz64(i, c);
+          tc::cp_async16(sb + o, src + c * 8);
+          tc::cp_async16(sb + 16384 + o, dsrc + c * 8);
+          if (kr >= 0 && kr < 128) {
+            const uint32_t ok = swz64(kr, c);
+            tc::cp_async16(sb + 32768 + ok, src + p.C + c * 8);
+            tc::cp_async16(sb + 40960 + ok, src + 2 * p.C + c * 8);
+          }
+        }
+      }
+      const float* lse_g = p.lse + (static_cast<long long>(s) * p.heads + head) * NP;
+      const float* dl_g = delta_g + (static_cast<long long>(s) * p.heads + head) * NP;
+      for (int i = lane; i < N / 4; i += 32) {
+        tc::cp_async16(sb + 49152 + i * 16, lse_g + i * 4);
+        tc::cp_async16(sb + 50176 + i * 16, dl_g + i * 4);
+      }
+      tc::cp_async_wait_all();
+      tc::fence_proxy_async();
+      tc::mbar_arrive(&ld_full[st]);
+    }
+  } else if (warp == 17) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = tc::make_idesc_bf16(128, QS, 0, 0);     // S^T, dP^T: A K-major, B K-major
+      const uint32_t idesc_kv = tc::make_idesc_bf16(128, HD, 0, 1);    // dV, dK: A TMEM, B MN-major
+      const uint32_t idesc_b = tc::make_idesc_bf16(128, 16, 0, 0);     // dBias: A TMEM, B = I16
+      const uint32_t idesc_q = tc::make_idesc_bf16(128, HD, 1, 1);     // dQ: A MN-major smem, B MN-major
+      const uint64_t idesc_ident = tc::make_smem_desc_sw64(tc::smem_u32(ident), 16, 512);
+      for (int T = 0; T <= TT; ++T) {
+        if (T < TT) {
+          const int n = T / NSUB, t = T % NSUB, st = n & 1, b = T & 1;
+          if (t == 0) tc::mbar_wait(&ld_full[st], (n >> 1) & 1);
+          tc::fence_after_sync();
+          const uint32_t sb = tc::smem_u32(stages + st * BWD_STAGE_BYTES);
+          const uint32_t d = tmem_base + COL_BUF + b * 64;
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            tc::mma_bf16_ss(d, tc::make_smem_desc_sw64(sb + 32768 + k * 32, 16, 512),
+                            tc::make_smem_desc_sw64(sb + t * (QS * 64) + k * 32, 16, 512), idesc_s, k);
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            tc::mma_bf16_ss(d + 32, tc::make_smem_desc_sw64(sb + 40960 + k * 32, 16, 512),
+                            tc::make_smem_desc_sw64(sb + 16384 + t * (QS * 64) + k * 32, 16, 512), idesc_s, k);
+          tc::mma_commit(&s_full[b]);
+        }
+        if (T >= 1) {
+          const int V = T - 1, n = V / NSUB, t = V % NSUB, st = n & 1, b = V & 1;
+          tc::mbar_wait(&p_ready[b], (V >> 1) & 1);
+          if (t == 0) tc::mbar_wait(acc_read, (n & 1) ^ 1);       // previous window's dK/dV/dQ were read out
+          tc::fence_after_sync();
+          const uint32_t sb = tc::smem_u32(stages + st * BWD_STAGE_BYTES);
+          const uint32_t a_p = tmem_base + COL_BUF + b * 64;        // P^T  (bf16 pairs: 8 columns per 16 queries, at 16*half)
+          const uint32_t a_ds = a_p + 32;                           // dS^T
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const uint32_t rows = (t * QS + k * 16) * 64;
+            tc::mma_bf16_ts(tmem_base + COL_DV, a_p + k * 16, tc::make_smem_desc_sw64(sb + 16384 + rows, 16, 512),
+                            idesc_kv, (t | k) ? 1u : 0u);
+            tc::mma_bf16_ts(tmem_base + COL_DK, a_ds + k * 16, tc::make_smem_desc_sw64(sb + rows, 16, 512),
+                            idesc_kv, (t | k) ? 1u : 0u);
+            tc::mma_bf16_ts(tmem_base + t * QS + k * 16, a_ds + k * 16, idesc_ident, idesc_b, n ? 1u : 0u);
+          }
+          if ((t & 3) == 3) {
+            // dQ for the 128-query block that is now complete in the smem tile
+            const int mb = t >> 2;
+            const uint32_t at = tc::smem_u32(ds_tile) + mb * 32768;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              tc::mma_bf16_ss(tmem_base + COL_DQ + mb * 32, tc::make_smem_desc_sw128(at + k * 2048, 16384, 1024),
+                              tc::make_smem_desc_sw64(sb + 32768 + k * 1024, 16, 512), idesc_q, k);
+            tc::mma_commit(&ds_free[mb]);
+            if (mb == 1) {
+              tc::mma_commit(unit_done);
+              tc::mma_commit(&ld_empty[st]);
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ compute groups
+    const int g = warp >> 3, q4 = warp & 3, half = (warp >> 2) & 1;
+    const int r = q4 * 32 + lane;                  // key row inside the half = TMEM lane
+    const int j = kh * 128 + r;                    // key token of the window
+    const int jb = j < N ? j : N - 1;
+    const uint32_t lane_addr = static_cast<uint32_t>(q4 * 32) << 16;
+    const float cscale = p.scale * LOG2E;
+    int rowbaseT;
+    {
+      const int dj = jb / (WH * WW), lr = jb - dj * (WH * WW), hj = lr / WW, wj = lr - hj * WW;
+      rowbaseT = ((WD - 1 - dj) * (2 * WH - 1) + (WH - 1 - hj)) * WW + wj;
+    }
+    // smem dS tile: element (query q, key r) at (q/64)*16384 + (r/8)*1024 + (r%8)*128 + (((q%64)/8) ^ (r%8))*16
+    const uint32_t ds_row = (r >> 3) * 1024 + (r & 7) * 128;
+
+    for (int T = g; T < TT; T += 2) {
+      const int n = T / NSUB, t = T % NSUB, st = n & 1;
+      const int s = blockIdx.x + n * gridDim.x;
+      const uint8_t* sb = stages + st * BWD_STAGE_BYTES;
+      const int q0 = t * QS + half * 16;
+
+      tc::mbar_wait(&s_full[g], (T >> 1) & 1);
+      tc::fence_after_sync();
+      float x[16], dp[16];
+      {
+        uint32_t u0[16], u1[16];
+        const uint32_t base = tmem_base + lane_addr + COL_BUF + g * 64 + half * 16;
+        tc::tmem_ld_32x32b_x16(base, u0);
+        tc::tmem_ld_32x32b_x16(base + 32, u1);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { x[k] = __uint_as_float(u0[k]); dp[k] = __uint_as_float(u1[k]); }
+      }
+      const int qr0 = q0 / WW;
+      switch (q0 % WW) {
+        case 0: add_bias_t16<WD, WH, WW, 0>(x, bias_s, rowbaseT, qr0, cscale); break;
+        case 2: add_bias_t16<WD, WH, WW, 2>(x, bias_s, rowbaseT, qr0, cscale); break;
+        default: add_bias_t16<WD, WH, WW, 4>(x, bias_s, rowbaseT, qr0, cscale); break;
+      }
+      if (window_masked(p, s)) {
+        const uint32_t ck4 = static_cast<uint32_t>(token_geom_t<WD, WH, WW>(p, s, jb).code) * 0x01010101u;
+        const uint4 qc = *reinterpret_cast<const uint4*>(sb + 51200 + q0);
+        const uint32_t qw[4] = {qc.x, qc.y, qc.z, qc.w};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const uint32_t ne = __vcmpne4(qw[w], ck4);
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const uint32_t m32 = __byte_perm(ne, 0, 0x8888u | (0x1111u * b));
+            x[w * 4 + b] += __uint_as_float(m32 & __float_as_uint(MASK_L2E));
+          }
+        }
+      }
+      uint32_t pk[8], dk[8];
+      {
+        const float4* l4 = reinterpret_cast<const float4*>(sb + 49152 + q0 * 4);
+        const float4* d4 = reinterpret_cast<const float4*>(sb + 50176 + q0 * 4);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 l = l4[c], dl = d4[c];
+          const float p0 = tc::ex2_approx(x[4 * c] - l.x), p1 = tc::ex2_approx(x[4 * c + 1] - l.y);
+          const float p2 = tc::ex2_approx(x[4 * c + 2] - l.z), p3 = tc::ex2_approx(x[4 * c + 3] - l.w);
+          pk[2 * c] = pack_bf16(p0, p1);
+          pk[2 * c + 1] = pack_bf16(p2, p3);
+          dk[2 * c] = pack_bf16(p0 * (dp[4 * c] - dl.x), p1 * (dp[4 * c + 1] - dl.y));
+          dk[2 * c + 1] = pack_bf16(p2 * (dp[4 * c + 2] - dl.z), p3 * (dp[4 * c + 3] - dl.w));
+        }
+      }
+      // P^T / dS^T over the first 8 of this thread's own 16 columns (bf16 pairs): TMEM A operands
+      const uint32_t pb = tmem_base + lane_addr + COL_BUF + g * 64 + half * 16;
+      tc::tmem_st_32x32b_x8(pb, pk);
+      tc::tmem_st_32x32b_x8(pb + 32, dk);
+      // dS^T copy for dQ; the previous window's dQ MMAs of this query block must be done with the tile
+      if ((t & 3) < 2) tc::mbar_wait(&ds_free[t >> 2], (n & 1) ^ 1);
+      {
+        uint8_t* dst = ds_tile + (q0 >> 6) * 16384 + ds_row;
+        const int c0 = (q0 & 63) >> 3;
+        *reinterpret_cast<uint4*>(dst + ((c0 ^ (r & 7)) << 4)) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
+        *reinterpret_cast<uint4*>(dst + (((c0 + 1) ^ (r & 7)) << 4)) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
+      }
+      tc::fence_proxy_async();
+      tc::tmem_st_wait();
+      tc::fence_before_sync();
+      tc::mbar_arrive(&p_ready[g]);
+
+      if (g == 1 && t == NSUB - 1) {
+        // ---- window read-out: dV / dK rows of this key half (direct stores), dQ partial (bf16x2 red.add)
+        tc::mbar_wait(unit_done, n & 1);
+        tc::fence_after_sync();
+        {
+          uint32_t acc[32];
+          tc::tmem_ld_32x32b_x32(tmem_base + lane_addr + (half ? COL_DK : COL_DV), acc);
+          tc::tmem_ld_wait();
+          if (j < N) {
+            const TokenGeom gk = token_geom_t<WD, WH, WW>(p, s, j);
+            const float sc = half ? p.scale : 1.f;
+            bf16* dst = p.dqkv + static_cast<long long>(gk.row) * (3LL * p.C) + (half ? p.C : 2 * p.C) + head * HD;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint4 w;
+              w.x = pack_bf16(__uint_as_float(acc[8 * c]) * sc, __uint_as_float(acc[8 * c + 1]) * sc);
+              w.y = pack_bf16(__uint_as_float(acc[8 * c + 2]) * sc, __uint_as_float(acc[8 * c + 3]) * sc);
+              w.z = pack_bf16(__uint_as_float(acc[8 * c + 4]) * sc, __uint_as_float(acc[8 * c + 5]) * sc);
+              w.w = pack_bf16(__uint_as_float(acc[8 * c + 6]) * sc, __uint_as_float(acc[8 * c + 7]) * sc);
+              reinterpret_cast<uint4*>(dst)[c] = w;
+            }
+          }
+          const int qi = half * 128 + r;      // query row of the dQ block this thread reads
+          tc::tmem_ld_32x32b_x32(tmem_base + lane_addr + COL_DQ + half * 32, acc);
+          tc::tmem_ld_wait();
+          tc::fence_before_sync();
+          tc::mbar_arrive(acc_read);
+          if (qi < N) {
+            const TokenGeom gq = token_geom_t<WD, WH, WW>(p, s, qi);
+            bf16* dst = p.dqkv + static_cast<long long>(gq.row) * (3LL * p.C) + head * HD;
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+              red_add_bf16x2(dst + 2 * c, pack_bf16(__uint_as_float(acc[2 * c]) * p.scale, __uint_as_float(acc[2 * c + 1]) * p.scale));
+          }
+        }
+      }
+    }
+    // ---- CTA end: flush the dense bias gradient of this (head, key half): dbias_dense[head][key][query]
+    if (p.dbias_dense != nullptr && TT > 0) {
+      // all MMAs of the CTA are complete once the last unit_done has fired (group 1 waited for it; group 0 waits here)
+      if (g == 0) tc::mbar_wait(unit_done, (n_units - 1) & 1);
+      tc::fence_after_sync();
+      float* dst = p.dbias_dense + (static_cast<long long>(head) * NP + jb) * NP + (g * 2 + half) * 64;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t acc[32];      // the TMEM load is warp-collective: never under a divergent branch
+        tc::tmem_ld_32x32b_x32(tmem_base + lane_addr + (g * 2 + half) * 64 + c * 32, acc);
+        tc::tmem_ld_wait();
+        if (j < N) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) atomicAdd(dst + c * 32 + k, __uint_as_float(acc[k]));
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 17) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// delta[s, head, i] = sum_e O[row(i), head*32+e] * dO[row(i), head*32+e]  (rowsum(dO * O) of the softmax backward)
+template <int WD, int WH, int WW>
+__global__ void __launch_bounds__(256) wattn_delta_kernel(const WinAttnArgs p, float* __restrict__ delta) {
+  constexpr int N = WD * WH * WW;
+  const int s = blockIdx.x;
+  for (int item = threadIdx.x; item < N * p.heads; item += blockDim.x) {
+    const int head = item % p.heads, i = item / p.heads;
+    const TokenGeom g = token_geom_t<WD, WH, WW>(p, s, i);
+    const uint4* o = reinterpret_cast<const uint4*>(p.out + static_cast<long long>(g.row) * p.C + head * HD);
+    const uint4* d = reinterpret_cast<const uint4*>(p.dout + static_cast<long long>(g.row) * p.C + head * HD);
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint4 a = o[c], b = d[c];
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 x = unpack_bf16(aw[t]), y = unpack_bf16(bw[t]);
+        acc = fmaf(x.x, y.x, fmaf(x.y, y.y, acc));
+      }
+    }
+    delta[(static_cast<long long>(s) * p.heads + head) * NP + i] = acc;
+  }
+}
+
+int wattn_tc_bwd(const WinAttnArgs& a, float* delta, cudaStream_t stream) {
+  using SM = BwdSmem<6, 7, 6>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VSN_CUDA(cudaFuncSetAttribute(wattn_bwd_kernel<6, 7, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    attr_set = true;
+  }
+  wattn_delta_kernel<6, 7, 6><<<a.S, 256, 0, stream>>>(a, delta);
+  VSN_LAUNCH_CHECK();
+  // dQ is accumulated by the two key-half CTAs with bf16x2 red.add: zero the Q block of dqkv first
+  VSN_CUDA(cudaMemset2DAsync(a.dqkv, 3LL * a.C * 2, 0, static_cast<size_t>(a.C) * 2,
+                             static_cast<size_t>(a.B) * a.Dp * a.Hp * a.Wp, stream));
+  int groups = vsn_num_sms() / (2 * a.heads);
+  if (groups < 1) groups = 1;
+  if (groups > a.S) groups = a.S;
+  groups = ceil_div(a.S, ceil_div(a.S, groups));
+  dim3 grid(groups, a.heads, 2);
+  wattn_bwd_kernel<6, 7, 6><<<grid, BWD_THREADS, SM::TOTAL, stream>>>(a, delta);
+  VSN_LAUNCH_CHECK();
+  return 0;
 }

@@ -21,4 +21,6 @@ struct WinAttnArgs {
 // true when the tcgen05 kernels cover this problem (head_dim 32, window (6,7,6))
 bool wattn_tc_supported(int wd, int wh, int ww, int hd);
 int wattn_tc_fwd(const WinAttnArgs& a, cudaStream_t stream);
-int wattn_tc_bwd(const WinAttnArgs& a, cudaStream_t stream);
+// delta [S, heads, 256] = rowsum(dO * O); lse is the log2-domain logsumexp written by wattn_tc_fwd;
+// dbias_dense is [heads][key][query] (transposed with respect to the mma.sync path).
+int wattn_tc_bwd(const WinAttnArgs& a, float* delta, cudaStream_t stream);
