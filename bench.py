@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--classes", type=int, default=3)
     ap.add_argument("--sam", action="store_true", help="SAM two-pass step (BASELINE config 3)")
     ap.add_argument("--no-ema", action="store_true")
+    ap.add_argument("--torch-ddp", action="store_true", help="N>1: use torch DDP instead of vsn_b200.ddp.GradAllReduce")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the instrumented pass (roofline = null)")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel table of the instrumented pass here")
@@ -230,11 +231,15 @@ def main():
                              stochastic_depth_prob=0.15, num_classes=args.classes, norm_layer=torch.nn.LayerNorm,
                              **SWIN).to(dev)
     model.train()
-    ddp = None
+    ddp, sync = None, None
     if world > 1:
-        ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], output_device=local,
-                                                        gradient_as_bucket_view=True)
-    ts = TrainStep(model, use_sam=args.sam, use_ema=not args.no_ema, ddp_model=ddp)
+        if args.torch_ddp:
+            ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], output_device=local,
+                                                            gradient_as_bucket_view=True)
+        else:
+            from vsn_b200.ddp import GradAllReduce
+            sync = GradAllReduce(model.parameters(), bucket_mb=25.0)
+    ts = TrainStep(model, use_sam=args.sam, use_ema=not args.no_ema, ddp_model=ddp, grad_sync=sync)
 
     G = args.micro_batches
     host = [synth_batch(args.batch, args.classes, seed=1234 + rank * 100 + i) for i in range(G)]

@@ -35,9 +35,10 @@ def param_groups(model: torch.nn.Module):
 class TrainStep:
     def __init__(self, model: torch.nn.Module, *, lr: float = 1e-4, weight_decay: float = 0.05, use_sam: bool = False,
                  sam_rho: float = 0.05, use_ema: bool = True, ema_decay: float = 0.999, smoothing: float = 0.1,
-                 ddp_model: Optional[torch.nn.Module] = None):
+                 ddp_model: Optional[torch.nn.Module] = None, grad_sync=None):
         self.module = model                       # the bare module (EMA / parameters)
         self.model = ddp_model if ddp_model is not None else model   # what forward is called on
+        self.grad_sync = grad_sync                # vsn_b200.ddp.GradAllReduce (bucketed NCCL all-reduce) or None
         groups = param_groups(model)
         if use_sam:
             self.opt = SAM(groups, torch.optim.AdamW, rho=sam_rho, adaptive=False, lr=lr, weight_decay=weight_decay,
@@ -52,23 +53,37 @@ class TrainStep:
         n = len(batches)
         total = None
         for i, (x, y) in enumerate(batches):
-            sync = i == n - 1 or not hasattr(self.model, "no_sync")
-            with (nullcontext() if sync else self.model.no_sync()):
+            last = i == n - 1
+            if self.grad_sync is not None:
+                ctx = nullcontext() if last else self.grad_sync.no_sync()
+            else:
+                ctx = nullcontext() if last or not hasattr(self.model, "no_sync") else self.model.no_sync()
+            with ctx:
                 loss = soft_target_ce(self.model(x), y, self.smoothing) / n
                 loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
+        if self.grad_sync is not None:
+            self.grad_sync.finish()               # gradients are now the cross-rank mean
         return total
+
+    def _zero_grad(self) -> None:
+        if self.grad_sync is not None:
+            self.grad_sync.zero_grad()            # .grad tensors are views into the flat buckets: keep them
+        else:
+            self.opt.zero_grad(set_to_none=True)
 
     def step(self, batches: Sequence[Tuple[torch.Tensor, torch.Tensor]]) -> torch.Tensor:
         """One optimiser step over the given micro-batches; returns the (device) loss of the first pass."""
         loss = self._accumulate(batches)
         if self.use_sam:
-            self.opt.first_step(zero_grad=True)
+            self.opt.first_step(zero_grad=False)
+            self._zero_grad()
             self._accumulate(batches)
-            self.opt.second_step(zero_grad=True)
+            self.opt.second_step(zero_grad=False)
+            self._zero_grad()
         else:
             self.opt.step()
-            self.opt.zero_grad(set_to_none=True)
+            self._zero_grad()
         if self.ema is not None:
             self.ema.update(self.module)
         return loss
