@@ -22,7 +22,9 @@ constexpr int A_BYTES = BM * BK * 2;
 struct GemmArgs {
   int M, N, K;          // output is M x N, reduction length K
   int a_mn, b_mn;       // operand majors (0 = K-major, 1 = MN-major)
-  int kb_per_split;     // k-blocks handled by one blockIdx.z
+  int kb_per_split;     // k-blocks handled by one split
+  int splits;           // K splits per output tile (fp32 atomic accumulation when > 1)
+  int total_tiles;      // tiles_m * tiles_n * splits
   void* out;
   long long ldo;
   int out_kind;         // 0 bf16 store, 1 fp32 store, 2 fp32 atomic add
@@ -41,37 +43,149 @@ template <int BN>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN <= 96) ? 4 : (BN <= 128 ? 3 : 2);
-  static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  static constexpr int STAGES = (196 * 1024) / STAGE_BYTES > 8 ? 8 : (196 * 1024) / STAGE_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;   // two accumulator buffers
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+constexpr int GEMM_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int EPI_THREADS = 256;
+
+struct TileCoord { int m0, n0, kb0, nkb; };
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmArgs& p, int tile, int tiles_n, int bn) {
+  const int split = tile % p.splits, mn = tile / p.splits;
+  TileCoord t;
+  t.n0 = (mn % tiles_n) * bn;
+  t.m0 = (mn / tiles_n) * BM;
+  const int nkb_total = (p.K + BK - 1) / BK;
+  t.kb0 = split * p.kb_per_split;
+  t.nkb = min(nkb_total, t.kb0 + p.kb_per_split) - t.kb0;
+  return t;
+}
+
+// One 32-column chunk of an output row: v = fp32 accumulators from TMEM.
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, int row, int n, float rs, const uint32_t* v) {
+  const int nvalid = min(32, p.N - n);
+  float f[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+  if (p.bias != nullptr) {
+    if (nvalid == 32) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(p.bias + n + j);
+        f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+      }
+    } else {
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { f[j] += p.bias[n + j]; }
+    }
+  }
+  if (p.act == 1) {
+    bf16* ap = p.aux + static_cast<long long>(row) * p.ldaux + n;
+    if (nvalid == 32) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 u;
+        u.x = pack_bf16(f[j], f[j + 1]); u.y = pack_bf16(f[j + 2], f[j + 3]);
+        u.z = pack_bf16(f[j + 4], f[j + 5]); u.w = pack_bf16(f[j + 6], f[j + 7]);
+        *reinterpret_cast<uint4*>(ap + j) = u;
+      }
+    } else {
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { ap[j] = __float2bfloat16(f[j]); }
+    }
+    // GELU is evaluated on the bf16-rounded pre-activation so backward (which only has the
+    // saved bf16 value) differentiates exactly the function forward applied.
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(__bfloat162float(__float2bfloat16(f[j])));
+  } else if (p.act == 2) {
+    const bf16* ap = p.aux + static_cast<long long>(row) * p.ldaux + n;
+    if (nvalid == 32) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        const uint4 u = *reinterpret_cast<const uint4*>(ap + j);
+        float2 t;
+        t = unpack_bf16(u.x); f[j] *= gelu_erf_grad(t.x); f[j + 1] *= gelu_erf_grad(t.y);
+        t = unpack_bf16(u.y); f[j + 2] *= gelu_erf_grad(t.x); f[j + 3] *= gelu_erf_grad(t.y);
+        t = unpack_bf16(u.z); f[j + 4] *= gelu_erf_grad(t.x); f[j + 5] *= gelu_erf_grad(t.y);
+        t = unpack_bf16(u.w); f[j + 6] *= gelu_erf_grad(t.x); f[j + 7] *= gelu_erf_grad(t.y);
+      }
+    } else {
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { f[j] *= gelu_erf_grad(__bfloat162float(ap[j])); }
+    }
+  }
+  if (rs != 1.0f) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] *= rs;
+  }
+  if (p.resid != nullptr) {
+    const float* rp = p.resid + static_cast<long long>(row) * p.ldr + n;
+    if (nvalid == 32) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
+        f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
+      }
+    } else {
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { f[j] += rp[j]; }
+    }
+  }
+  if (p.out_kind == 0) {
+    bf16* op = reinterpret_cast<bf16*>(p.out) + static_cast<long long>(row) * p.ldo + n;
+    if (nvalid == 32) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 u;
+        u.x = pack_bf16(f[j], f[j + 1]); u.y = pack_bf16(f[j + 2], f[j + 3]);
+        u.z = pack_bf16(f[j + 4], f[j + 5]); u.w = pack_bf16(f[j + 6], f[j + 7]);
+        *reinterpret_cast<uint4*>(op + j) = u;
+      }
+    } else {
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { op[j] = __float2bfloat16(f[j]); }
+    }
+  } else if (p.out_kind == 1) {
+    float* op = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + n;
+    if (nvalid == 32) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+    } else {
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { op[j] = f[j]; }
+    }
+  } else {
+    float* op = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + n;
+    _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { atomicAdd(op + j, f[j]); }
+  }
+}
+
+// Persistent: CTA b works on tiles b, b + gridDim.x, ...  The TMA ring runs ahead across tile boundaries and the
+// accumulator is double-buffered in TMEM, so the MMAs of tile i+1 overlap the epilogue of tile i.
 template <int BN>
-__global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                      const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                   const __grid_constant__ CUtensorMap tmB,
+                                                                   const GemmArgs p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
-  uint64_t* accum_bar = empty_bar + C::STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* acc_full = empty_bar + C::STAGES;     // [2] MMA commit -> epilogue
+  uint64_t* acc_empty = acc_full + 2;             // [2] epilogue threads -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM;
-  const int n0 = blockIdx.y * BN;
-  const int nkb_total = (p.K + BK - 1) / BK;
-  const int kb0 = blockIdx.z * p.kb_per_split;
-  const int kb1 = min(nkb_total, kb0 + p.kb_per_split);
-  const int nkb = kb1 - kb0;
+  const int tiles_n = (p.N + BN - 1) / BN;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       tc::mbar_init(&full_bar[s], 1);
       tc::mbar_init(&empty_bar[s], 1);
     }
-    tc::mbar_init(accum_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(&acc_full[b], 1);
+      tc::mbar_init(&acc_empty[b], EPI_THREADS);
+    }
     tc::fence_barrier_init();
     tc::prefetch_tmap(&tmA);
     tc::prefetch_tmap(&tmB);
@@ -82,164 +196,94 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (nkb > 0) {
-    if (warp == 0) {
-      if (lane == 0) {
-        for (int i = 0; i < nkb; ++i) {
-          const int s = i % C::STAGES;
-          const uint32_t ph = (i / C::STAGES) & 1;
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;   // k-blocks issued so far (ring position)
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile, tiles_n, BN);
+        for (int i = 0; i < t.nkb; ++i, ++it) {
+          const int s = it % C::STAGES;
+          const uint32_t ph = (it / C::STAGES) & 1;
           tc::mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * C::STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           tc::mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
-          const int k0 = (kb0 + i) * BK;
+          const int k0 = (t.kb0 + i) * BK;
           if (!p.a_mn) {
-            tc::tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);           // box {64 k, 128 rows}
+            tc::tma_load_2d(sa, &tmA, &full_bar[s], k0, t.m0);           // box {64 k, 128 rows}
           } else {
-            tc::tma_load_2d(sa, &tmA, &full_bar[s], m0, k0);           // box {64 m, 64 k-rows}
-            tc::tma_load_2d(sa + 8192, &tmA, &full_bar[s], m0 + 64, k0);
+            tc::tma_load_2d(sa, &tmA, &full_bar[s], t.m0, k0);           // box {64 m, 64 k-rows}
+            tc::tma_load_2d(sa + 8192, &tmA, &full_bar[s], t.m0 + 64, k0);
           }
           if (!p.b_mn) {
-            tc::tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);           // box {64 k, BN rows}
+            tc::tma_load_2d(sb, &tmB, &full_bar[s], k0, t.n0);           // box {64 k, BN rows}
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tc::tma_load_2d(sb + j * 8192, &tmB, &full_bar[s], n0 + j * 64, k0);
+            for (int j = 0; j < BN / 64; ++j) tc::tma_load_2d(sb + j * 8192, &tmB, &full_bar[s], t.n0 + j * 64, k0);
           }
         }
       }
-    } else if (warp == 1) {
-      if (lane == 0) {
-        const uint32_t idesc = tc::make_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
-        const uint32_t a_step = p.a_mn ? 2048u : 32u;   // bytes per K=16 step
-        const uint32_t b_step = p.b_mn ? 2048u : 32u;
-        const uint32_t a_lbo = p.a_mn ? 8192u : 16u;
-        const uint32_t b_lbo = p.b_mn ? 8192u : 16u;
-        for (int i = 0; i < nkb; ++i) {
-          const int s = i % C::STAGES;
-          const uint32_t ph = (i / C::STAGES) & 1;
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+      const uint32_t a_step = p.a_mn ? 2048u : 32u;   // bytes per K=16 step
+      const uint32_t b_step = p.b_mn ? 2048u : 32u;
+      const uint32_t a_lbo = p.a_mn ? 8192u : 16u;
+      const uint32_t b_lbo = p.b_mn ? 8192u : 16u;
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+        const TileCoord t = decode_tile(p, tile, tiles_n, BN);
+        const int buf = lt & 1;
+        tc::mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);
+        tc::fence_after_sync();
+        const uint32_t d = tmem_base + buf * BN;
+        for (int i = 0; i < t.nkb; ++i, ++it) {
+          const int s = it % C::STAGES;
+          const uint32_t ph = (it / C::STAGES) & 1;
           tc::mbar_wait(&full_bar[s], ph);
           tc::fence_after_sync();
           const uint32_t sa = tc::smem_u32(smem + s * C::STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
-          const int krem = p.K - (kb0 + i) * BK;
+          const int krem = p.K - (t.kb0 + i) * BK;
           const int ksteps = krem >= BK ? BK / 16 : (krem + 15) / 16;
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t ad = tc::make_smem_desc_sw128(sa + k * a_step, a_lbo, 1024);
             const uint64_t bd = tc::make_smem_desc_sw128(sb + k * b_step, b_lbo, 1024);
-            tc::mma_bf16_ss(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            tc::mma_bf16_ss(d, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
           }
           tc::mma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs retire
         }
-        tc::mma_commit(accum_bar);         // accumulator complete
+        tc::mma_commit(&acc_full[buf]);    // accumulator complete
       }
-    } else {
-      // ---- epilogue: thread <-> output row --------------------------------------------
-      const int lg = warp & 3;                     // TMEM lane group this warp may touch
-      const int row = m0 + lg * 32 + lane;
-      tc::mbar_wait(accum_bar, 0);
+    }
+  } else {
+    // ---- epilogue: thread <-> output row; warps 2-5 take the even 32-column chunks, 6-9 the odd ones ----
+    const int lg = warp & 3;                     // TMEM lane group this warp may touch
+    const int par = (warp - 2) >> 2;             // chunk parity
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      const TileCoord t = decode_tile(p, tile, tiles_n, BN);
+      const int buf = lt & 1;
+      const int row = t.m0 + lg * 32 + lane;
+      tc::mbar_wait(&acc_full[buf], (lt >> 1) & 1);
       tc::fence_after_sync();
       const bool row_ok = row < p.M;
       float rs = p.alpha;
       if (p.row_scale != nullptr && row_ok) rs *= p.row_scale[row / p.rows_per_group];
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = par * 32; c0 < BN; c0 += 64) {
         uint32_t v[32];
-        tc::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + c0, v);
+        tc::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + buf * BN + c0, v);
         tc::tmem_ld_wait();
-        const int n = n0 + c0;
-        if (!row_ok || n >= p.N) continue;
-        const int nvalid = min(32, p.N - n);
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias != nullptr) {
-          if (nvalid == 32) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(p.bias + n + j);
-              f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-            }
-          } else {
-            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { f[j] += p.bias[n + j]; }
-          }
-        }
-        if (p.act == 1) {
-          bf16* ap = p.aux + static_cast<long long>(row) * p.ldaux + n;
-          if (nvalid == 32) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 u;
-              u.x = pack_bf16(f[j], f[j + 1]); u.y = pack_bf16(f[j + 2], f[j + 3]);
-              u.z = pack_bf16(f[j + 4], f[j + 5]); u.w = pack_bf16(f[j + 6], f[j + 7]);
-              *reinterpret_cast<uint4*>(ap + j) = u;
-            }
-          } else {
-            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { ap[j] = __float2bfloat16(f[j]); }
-          }
-          // GELU is evaluated on the bf16-rounded pre-activation so backward (which only has the
-          // saved bf16 value) differentiates exactly the function forward applied.
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(__bfloat162float(__float2bfloat16(f[j])));
-        } else if (p.act == 2) {
-          const bf16* ap = p.aux + static_cast<long long>(row) * p.ldaux + n;
-          if (nvalid == 32) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const uint4 u = *reinterpret_cast<const uint4*>(ap + j);
-              float2 t;
-              t = unpack_bf16(u.x); f[j] *= gelu_erf_grad(t.x); f[j + 1] *= gelu_erf_grad(t.y);
-              t = unpack_bf16(u.y); f[j + 2] *= gelu_erf_grad(t.x); f[j + 3] *= gelu_erf_grad(t.y);
-              t = unpack_bf16(u.z); f[j + 4] *= gelu_erf_grad(t.x); f[j + 5] *= gelu_erf_grad(t.y);
-              t = unpack_bf16(u.w); f[j + 6] *= gelu_erf_grad(t.x); f[j + 7] *= gelu_erf_grad(t.y);
-            }
-          } else {
-            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { f[j] *= gelu_erf_grad(__bfloat162float(ap[j])); }
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] *= rs;
-        if (p.resid != nullptr) {
-          const float* rp = p.resid + static_cast<long long>(row) * p.ldr + n;
-          if (nvalid == 32) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
-              f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
-            }
-          } else {
-            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { f[j] += rp[j]; }
-          }
-        }
-        if (p.out_kind == 0) {
-          bf16* op = reinterpret_cast<bf16*>(p.out) + static_cast<long long>(row) * p.ldo + n;
-          if (nvalid == 32) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 u;
-              u.x = pack_bf16(f[j], f[j + 1]); u.y = pack_bf16(f[j + 2], f[j + 3]);
-              u.z = pack_bf16(f[j + 4], f[j + 5]); u.w = pack_bf16(f[j + 6], f[j + 7]);
-              *reinterpret_cast<uint4*>(op + j) = u;
-            }
-          } else {
-            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { op[j] = __float2bfloat16(f[j]); }
-          }
-        } else if (p.out_kind == 1) {
-          float* op = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + n;
-          if (nvalid == 32) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          } else {
-            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { op[j] = f[j]; }
-          }
-        } else {
-          float* op = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + n;
-          _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { atomicAdd(op + j, f[j]); }
-        }
+        const int n = t.n0 + c0;
+        if (row_ok && n < p.N) epilogue_chunk(p, row, n, rs, v);
       }
       tc::fence_before_sync();
+      tc::mbar_arrive(&acc_empty[buf]);
     }
   }
+  tc::fence_before_sync();
   __syncthreads();
   if (warp == 1) {
     tc::fence_after_sync();
@@ -283,14 +327,16 @@ int make_tmap_2d(CUtensorMap* map, const void* base, long long dim0, long long d
 }
 
 template <int BN>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, int splits, cudaStream_t stream) {
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs a, int splits, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     VSN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
     attr_set = true;
   }
-  dim3 grid(ceil_div(a.M, BM), ceil_div(a.N, BN), splits);
-  gemm_tc_kernel<BN><<<grid, 192, Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, a);
+  a.splits = splits;
+  a.total_tiles = ceil_div(a.M, BM) * ceil_div(a.N, BN) * splits;
+  const int grid = a.total_tiles < vsn_num_sms() ? a.total_tiles : vsn_num_sms();
+  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, a);
   VSN_LAUNCH_CHECK();
   return 0;
 }
@@ -307,14 +353,27 @@ extern "C" int vsn_gemm_bf16(const void* A, long long lda, int a_mn, const void*
   VSN_CHECK(split_k <= 1 || out_kind == 2, "vsn_gemm_bf16: split_k needs atomic fp32 output");
   VSN_CHECK(out_kind != 2 || (bias == nullptr && act == 0 && resid == nullptr),
             "vsn_gemm_bf16: atomic output takes no bias/activation/residual");
+  // Tile width: the widest of {256, 192, 128, 96, 64} that divides N (an MN-major B operand is loaded in
+  // 64-column blocks), falling back to smaller tiles while the problem has fewer tiles than SMs.
   int BN;
-  if (b_mn) BN = (N <= 64) ? 64 : 128;
+  if (b_mn) BN = (N % 256 == 0) ? 256 : (N % 192 == 0) ? 192 : (N <= 64) ? 64 : 128;
+  else if (N % 256 == 0) BN = 256;
+  else if (N % 192 == 0) BN = 192;
   else if (N % 128 == 0) BN = 128;
   else if (N % 96 == 0) BN = 96;
   else if (N <= 64) BN = 64;
   else if (N <= 96) BN = 96;
   else BN = 128;
-
+  {
+    const int want = vsn_num_sms();
+    const int sk = split_k < 1 ? 1 : split_k;
+    while (BN > 64 && ceil_div(M, BM) * ceil_div(N, BN) * sk < want) {
+      const int next = BN == 256 ? 128 : BN == 192 ? (b_mn ? 64 : 96) : BN == 128 ? 64 : BN == 96 ? (N % 64 == 0 || N <= 64 ? 64 : 96) : 64;
+      if (next == BN) break;
+      if (N % next != 0 && next < N) break;   // keep tiles exact when they were exact
+      BN = next;
+    }
+  }
   CUtensorMap tmA, tmB;
   int rc;
   if (!a_mn) rc = make_tmap_2d(&tmA, A, K, M, lda, BK, BM);
@@ -339,6 +398,8 @@ extern "C" int vsn_gemm_bf16(const void* A, long long lda, int a_mn, const void*
   switch (BN) {
     case 64: return launch<64>(tmA, tmB, a, splits, s);
     case 96: return launch<96>(tmA, tmB, a, splits, s);
+    case 192: return launch<192>(tmA, tmB, a, splits, s);
+    case 256: return launch<256>(tmA, tmB, a, splits, s);
     default: return launch<128>(tmA, tmB, a, splits, s);
   }
 }
