@@ -50,11 +50,12 @@ int vsn_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lo
  * models/vit_3d.py:69,98,129,371,373,401.  x fp32 rows; y bf16 (y_bf16=1) or fp32; mean/rstd [rows]. */
 int vsn_layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, void* y, long long ldy,
                       int y_bf16, float* mean, float* rstd, long long rows, int C, float eps, void* stream);
-/* dx = LN'(dy) (+ resid_grad); optional bf16 copy of dx scaled per row group (DropPath of the consumer). */
+/* dx = LN'(dy) (+ resid_grad); optional bf16 copy of dx scaled per row group (DropPath of the consumer);
+ * dgamma/dbeta [C] fp32 (both or neither): += sum_r dy*xhat, += sum_r dy, fused in the same pass over dy and x. */
 int vsn_layernorm_bwd(const void* dy, long long lddy, int dy_bf16, const float* x, long long ldx, const float* mean,
                       const float* rstd, const float* gamma, const float* resid_grad, long long ldr, float* dx,
                       long long lddx, void* dx_bf16, long long ldb, const float* row_scale, int rows_per_group,
-                      long long rows, int C, void* stream);
+                      float* dgamma, float* dbeta, long long rows, int C, void* stream);
 /* dgamma[c] += sum_r dy*xhat, dbeta[c] += sum_r dy (x != NULL); plain column sum into dbeta when x == NULL
  * (the bias gradients of every Linear / Conv3d on the path). */
 int vsn_colreduce(const void* dy, long long lddy, int dy_bf16, const float* x, long long ldx, const float* mean,

@@ -81,7 +81,8 @@ def test_gemm_dgrad_wgrad(M, N, K):
 
 
 # ----------------------------------------------------------------------------- LayerNorm
-@pytest.mark.parametrize("rows,C", [(1000, 96), (333, 768), (50, 3072), (17, 4096), (4000, 192)])
+@pytest.mark.parametrize("rows,C", [(1000, 96), (333, 768), (50, 3072), (17, 4096), (4000, 192), (70001, 96),
+                                    (9, 384), (5000, 1536), (131, 64), (777, 128), (40000, 384)])
 def test_layernorm(rows, C):
     ops = _ops()
     x, g, b = _rand(rows, C, seed=1) * 2 + 0.5, 1 + 0.1 * _rand(C, seed=2), 0.1 * _rand(C, seed=3)
@@ -101,6 +102,13 @@ def test_layernorm(rows, C):
     dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
     ops.ln_param_grad(dy, x, mean, rstd, dg, db)
     assert rel_err(dg, gr.grad) < 1e-4 and rel_err(db, br.grad) < 1e-4
+    # parameter gradients fused into the backward pass (accumulating)
+    dg2, db2 = dg.clone(), db.clone()
+    dx2, _ = ops.layernorm_bwd(_bf(dy), x, mean, rstd, g, dgamma=dg2, dbeta=db2)
+    assert rel_err(dx2, xr.grad) < BF16_TOL
+    gr.grad = None; br.grad = None; xr.grad = None
+    torch.nn.functional.layer_norm(xr, (C,), gr, br, 1e-5).backward(_bf(dy).float())
+    assert rel_err(dg2 - dg, gr.grad) < 1e-4 and rel_err(db2 - db, br.grad) < 1e-4
     cs = torch.zeros(C, device="cuda")
     ops.colsum(_bf(dy), cs)
     assert rel_err(cs, _bf(dy).float().sum(0)) < 1e-4

@@ -18,7 +18,7 @@ SIGNATURES = {
     "vsn_check_device": [],
     "vsn_gemm_bf16": [_p, _ll, _i, _p, _ll, _i, _i, _i, _i, _p, _ll, _i, _p, _i, _p, _ll, _p, _ll, _p, _i, _f, _i, _p],
     "vsn_layernorm_fwd": [_p, _ll, _p, _p, _p, _ll, _i, _p, _p, _ll, _i, _f, _p],
-    "vsn_layernorm_bwd": [_p, _ll, _i, _p, _ll, _p, _p, _p, _p, _ll, _p, _ll, _p, _ll, _p, _i, _ll, _i, _p],
+    "vsn_layernorm_bwd": [_p, _ll, _i, _p, _ll, _p, _p, _p, _p, _ll, _p, _ll, _p, _ll, _p, _i, _p, _p, _ll, _i, _p],
     "vsn_colreduce": [_p, _ll, _i, _p, _ll, _p, _p, _p, _p, _ll, _i, _p],
     "vsn_attn_fwd": [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _f, _p],
     "vsn_attn_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _f, _p],

@@ -183,6 +183,189 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const DyT* __rest
   }
 }
 
+
+// ---- fast paths: C == LPR * V * 4 (LPR lanes per row, V float4 per lane) -------------------------------------
+// A row is held entirely in registers by a group of LPR lanes (32/LPR rows per warp), every lane issues V
+// independent 16-byte loads, and the row statistics are butterfly reductions inside the group.
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename OutT, int LPR, int V>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_fast_kernel(const float* __restrict__ x, long long ldx,
+                                                                    const float* __restrict__ gamma,
+                                                                    const float* __restrict__ beta, OutT* __restrict__ y,
+                                                                    long long ldy, float* __restrict__ mean_out,
+                                                                    float* __restrict__ rstd_out, long long rows, float eps) {
+  constexpr int C = LPR * V * 4;
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, l = lane % LPR;
+  const long long row = (static_cast<long long>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5)) * RPW + lane / LPR;
+  const bool ok = row < rows;
+  const float* xr = x + (ok ? row : 0) * ldx;
+  float4 v[V];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    v[i] = ok ? *reinterpret_cast<const float4*>(xr + 4 * (l + LPR * i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mu = group_sum<LPR>(s) * (1.0f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(group_sum<LPR>(q) * (1.0f / C) + eps);
+  if (!ok) return;
+  OutT* yr = y + row * ldy;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int j = 4 * (l + LPR * i);
+    const float4 g = *reinterpret_cast<const float4*>(gamma + j);
+    const float4 b = *reinterpret_cast<const float4*>(beta + j);
+    const float o0 = (v[i].x - mu) * rstd * g.x + b.x, o1 = (v[i].y - mu) * rstd * g.y + b.y;
+    const float o2 = (v[i].z - mu) * rstd * g.z + b.z, o3 = (v[i].w - mu) * rstd * g.w + b.w;
+    if constexpr (sizeof(OutT) == 2) {
+      uint2 u;
+      u.x = pack_bf16(o0, o1);
+      u.y = pack_bf16(o2, o3);
+      *reinterpret_cast<uint2*>(yr + j) = u;
+    } else {
+      *reinterpret_cast<float4*>(yr + j) = make_float4(o0, o1, o2, o3);
+    }
+  }
+  if (l == 0) {
+    if (mean_out) mean_out[row] = mu;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+}
+
+// Backward with the parameter gradients fused: every lane owns fixed columns for all the rows it visits
+// (persistent row loop), accumulates dgamma / dbeta for them in registers, and the block adds its partial
+// sums to global memory once (C atomics per block) -- dy and x are read exactly once.
+template <typename DyT, int LPR, int V>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_fast_kernel(const DyT* __restrict__ dy, long long lddy,
+                                                                    const float* __restrict__ x, long long ldx,
+                                                                    const float* __restrict__ mean,
+                                                                    const float* __restrict__ rstd,
+                                                                    const float* __restrict__ gamma,
+                                                                    const float* __restrict__ resid_grad, long long ldr,
+                                                                    float* __restrict__ dx, long long lddx,
+                                                                    bf16* __restrict__ dx_bf16, long long ldb,
+                                                                    const float* __restrict__ row_scale,
+                                                                    int rows_per_group, long long rows,
+                                                                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  constexpr int C = LPR * V * 4;
+  constexpr int RPW = 32 / LPR;
+  __shared__ float red[LN_WARPS][C + 4];
+  const int lane = threadIdx.x & 31, l = lane % LPR, warp = threadIdx.x >> 5;
+  float4 g[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) g[i] = *reinterpret_cast<const float4*>(gamma + 4 * (l + LPR * i));
+  float4 ag[V], ab[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool want_pg = dgamma != nullptr;
+  const long long stride = static_cast<long long>(gridDim.x) * LN_WARPS * RPW;
+  for (long long row = (static_cast<long long>(blockIdx.x) * LN_WARPS + warp) * RPW + lane / LPR;
+       row - lane / LPR < rows; row += stride) {
+    const bool ok = row < rows;
+    const long long r = ok ? row : 0;
+    const float mu = mean[r], rs = rstd[r];
+    float4 xv[V], d[V];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int j = 4 * (l + LPR * i);
+      xv[i] = *reinterpret_cast<const float4*>(x + r * ldx + j);
+      if constexpr (sizeof(DyT) == 2) {
+        const uint2 u = *reinterpret_cast<const uint2*>(dy + r * lddy + j);
+        const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+        d[i] = make_float4(a.x, a.y, b.x, b.y);
+      } else {
+        d[i] = *reinterpret_cast<const float4*>(dy + r * lddy + j);
+      }
+      if (!ok) d[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      xv[i].x = (xv[i].x - mu) * rs; xv[i].y = (xv[i].y - mu) * rs;      // xhat
+      xv[i].z = (xv[i].z - mu) * rs; xv[i].w = (xv[i].w - mu) * rs;
+      if (want_pg) {
+        ab[i].x += d[i].x; ab[i].y += d[i].y; ab[i].z += d[i].z; ab[i].w += d[i].w;
+        ag[i].x = fmaf(d[i].x, xv[i].x, ag[i].x); ag[i].y = fmaf(d[i].y, xv[i].y, ag[i].y);
+        ag[i].z = fmaf(d[i].z, xv[i].z, ag[i].z); ag[i].w = fmaf(d[i].w, xv[i].w, ag[i].w);
+      }
+      d[i].x *= g[i].x; d[i].y *= g[i].y; d[i].z *= g[i].z; d[i].w *= g[i].w;
+      s1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
+      s2 += (d[i].x * xv[i].x + d[i].y * xv[i].y) + (d[i].z * xv[i].z + d[i].w * xv[i].w);
+    }
+    s1 = group_sum<LPR>(s1) * (1.0f / C);
+    s2 = group_sum<LPR>(s2) * (1.0f / C);    // mean(dy*g*xhat)
+    if (!ok) continue;
+    float scale = 1.f;
+    if (dx_bf16 != nullptr && row_scale != nullptr) scale = row_scale[row / rows_per_group];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int j = 4 * (l + LPR * i);
+      float o0 = rs * (d[i].x - s1 - xv[i].x * s2), o1 = rs * (d[i].y - s1 - xv[i].y * s2);
+      float o2 = rs * (d[i].z - s1 - xv[i].z * s2), o3 = rs * (d[i].w - s1 - xv[i].w * s2);
+      if (resid_grad != nullptr) {
+        const float4 rg = *reinterpret_cast<const float4*>(resid_grad + row * ldr + j);
+        o0 += rg.x; o1 += rg.y; o2 += rg.z; o3 += rg.w;
+      }
+      if (dx != nullptr) *reinterpret_cast<float4*>(dx + row * lddx + j) = make_float4(o0, o1, o2, o3);
+      if (dx_bf16 != nullptr) {
+        uint2 u;
+        u.x = pack_bf16(o0 * scale, o1 * scale);
+        u.y = pack_bf16(o2 * scale, o3 * scale);
+        *reinterpret_cast<uint2*>(dx_bf16 + row * ldb + j) = u;
+      }
+    }
+  }
+  if (!want_pg) return;
+  // fold the row groups of the warp, then the warps of the block (smem, dgamma then dbeta), then one atomic
+  // per column and block
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+      ag[i].x += __shfl_xor_sync(0xffffffffu, ag[i].x, o); ag[i].y += __shfl_xor_sync(0xffffffffu, ag[i].y, o);
+      ag[i].z += __shfl_xor_sync(0xffffffffu, ag[i].z, o); ag[i].w += __shfl_xor_sync(0xffffffffu, ag[i].w, o);
+      ab[i].x += __shfl_xor_sync(0xffffffffu, ab[i].x, o); ab[i].y += __shfl_xor_sync(0xffffffffu, ab[i].y, o);
+      ab[i].z += __shfl_xor_sync(0xffffffffu, ab[i].z, o); ab[i].w += __shfl_xor_sync(0xffffffffu, ab[i].w, o);
+    }
+  }
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    if (lane < LPR) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) *reinterpret_cast<float4*>(&red[warp][4 * (l + LPR * i)]) = which ? ab[i] : ag[i];
+    }
+    __syncthreads();
+    for (int col = threadIdx.x; col < C; col += LN_WARPS * 32) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < LN_WARPS; ++w) t += red[w][col];
+      atomicAdd((which ? dbeta : dgamma) + col, t);
+    }
+    __syncthreads();
+  }
+}
+
+struct LnShape { int lpr, v; };
+__host__ inline LnShape ln_fast_shape(int C) {
+  static const int table[][2] = {{8, 2}, {8, 3}, {8, 4}, {16, 3}, {16, 4}, {32, 3}, {32, 4}, {32, 6}};
+  for (const auto& t : table)
+    if (t[0] * t[1] * 4 == C) return {t[0], t[1]};
+  return {0, 0};
+}
+
 // Column reductions over rows: dbeta[c] += sum_r dy[r,c]; dgamma[c] += sum_r dy[r,c]*xhat[r,c].
 // With x == nullptr it is a plain column sum (bias gradients of the Linear layers).
 constexpr int CR_TX = 32, CR_TY = 8, CR_ROWS = 256;
@@ -222,13 +405,33 @@ __global__ void __launch_bounds__(CR_TX * CR_TY) colreduce_kernel(const DyT* __r
 
 }  // namespace
 
+extern "C" int vsn_colreduce(const void* dy, long long lddy, int dy_bf16, const float* x, long long ldx,
+                             const float* mean, const float* rstd, float* dgamma, float* dbeta, long long rows, int C,
+                             void* stream);
+
 extern "C" int vsn_layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, void* y,
                                  long long ldy, int y_bf16, float* mean, float* rstd, long long rows, int C,
                                  float eps, void* stream) {
   VSN_CHECK(C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "vsn_layernorm_fwd: C/ld must be multiples of 4 (C=%d)", C);
   if (rows == 0) return 0;
-  const unsigned grid = static_cast<unsigned>(ceil_div_ll(rows, LN_WARPS));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const LnShape fs = ln_fast_shape(C);
+  if (fs.lpr != 0) {
+    const unsigned g2 = static_cast<unsigned>(ceil_div_ll(rows, LN_WARPS * (32 / fs.lpr)));
+#define VSN_LN_FWD(L, VV)                                                                                         \
+    if (fs.lpr == L && fs.v == VV) {                                                                                \
+      if (y_bf16) ln_fwd_fast_kernel<bf16, L, VV><<<g2, LN_WARPS * 32, 0, s>>>(x, ldx, gamma, beta,                 \
+                      reinterpret_cast<bf16*>(y), ldy, mean, rstd, rows, eps);                                      \
+      else ln_fwd_fast_kernel<float, L, VV><<<g2, LN_WARPS * 32, 0, s>>>(x, ldx, gamma, beta,                       \
+                      reinterpret_cast<float*>(y), ldy, mean, rstd, rows, eps);                                     \
+    }
+    VSN_LN_FWD(8, 2) VSN_LN_FWD(8, 3) VSN_LN_FWD(8, 4) VSN_LN_FWD(16, 3) VSN_LN_FWD(16, 4)
+    VSN_LN_FWD(32, 3) VSN_LN_FWD(32, 4) VSN_LN_FWD(32, 6)
+#undef VSN_LN_FWD
+    VSN_LAUNCH_CHECK();
+    return 0;
+  }
+  const unsigned grid = static_cast<unsigned>(ceil_div_ll(rows, LN_WARPS));
   if (y_bf16)
     ln_fwd_kernel<bf16><<<grid, LN_WARPS * 32, 0, s>>>(x, ldx, gamma, beta, reinterpret_cast<bf16*>(y), ldy, mean,
                                                          rstd, rows, C, eps);
@@ -242,12 +445,37 @@ extern "C" int vsn_layernorm_fwd(const float* x, long long ldx, const float* gam
 extern "C" int vsn_layernorm_bwd(const void* dy, long long lddy, int dy_bf16, const float* x, long long ldx,
                                  const float* mean, const float* rstd, const float* gamma, const float* resid_grad,
                                  long long ldr, float* dx, long long lddx, void* dx_bf16, long long ldb,
-                                 const float* row_scale, int rows_per_group, long long rows, int C, void* stream) {
+                                 const float* row_scale, int rows_per_group, float* dgamma, float* dbeta,
+                                 long long rows, int C, void* stream) {
   VSN_CHECK(C % 4 == 0, "vsn_layernorm_bwd: C must be a multiple of 4 (C=%d)", C);
+  VSN_CHECK((dgamma == nullptr) == (dbeta == nullptr), "vsn_layernorm_bwd: dgamma and dbeta go together");
   if (rows == 0) return 0;
-  const unsigned grid = static_cast<unsigned>(ceil_div_ll(rows, LN_WARPS));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int rpg = rows_per_group > 0 ? rows_per_group : 1;
+  const LnShape fs = ln_fast_shape(C);
+  if (fs.lpr != 0 && lddy % 4 == 0 && ldx % 4 == 0) {
+    const long long need = ceil_div_ll(rows, LN_WARPS * (32 / fs.lpr));
+    const long long cap = 4LL * vsn_num_sms();
+    const unsigned g2 = static_cast<unsigned>(need < cap ? need : cap);
+#define VSN_LN_BWD(L, VV)                                                                                          \
+    if (fs.lpr == L && fs.v == VV) {                                                                                 \
+      if (dy_bf16) ln_bwd_fast_kernel<bf16, L, VV><<<g2, LN_WARPS * 32, 0, s>>>(reinterpret_cast<const bf16*>(dy), lddy, \
+                      x, ldx, mean, rstd, gamma, resid_grad, ldr, dx, lddx, reinterpret_cast<bf16*>(dx_bf16), ldb,   \
+                      row_scale, rpg, rows, dgamma, dbeta);                                                          \
+      else ln_bwd_fast_kernel<float, L, VV><<<g2, LN_WARPS * 32, 0, s>>>(reinterpret_cast<const float*>(dy), lddy,  \
+                      x, ldx, mean, rstd, gamma, resid_grad, ldr, dx, lddx, reinterpret_cast<bf16*>(dx_bf16), ldb,   \
+                      row_scale, rpg, rows, dgamma, dbeta);                                                          \
+    }
+    VSN_LN_BWD(8, 2) VSN_LN_BWD(8, 3) VSN_LN_BWD(8, 4) VSN_LN_BWD(16, 3) VSN_LN_BWD(16, 4)
+    VSN_LN_BWD(32, 3) VSN_LN_BWD(32, 4) VSN_LN_BWD(32, 6)
+#undef VSN_LN_BWD
+    VSN_LAUNCH_CHECK();
+    return 0;
+  }
+  if (dgamma != nullptr) {   // generic shapes: separate column reduction, then the row kernel
+    if (int rc = vsn_colreduce(dy, lddy, dy_bf16, x, ldx, mean, rstd, dgamma, dbeta, rows, C, stream)) return rc;
+  }
+  const unsigned grid = static_cast<unsigned>(ceil_div_ll(rows, LN_WARPS));
   if (dy_bf16)
     ln_bwd_kernel<bf16><<<grid, LN_WARPS * 32, 0, s>>>(reinterpret_cast<const bf16*>(dy), lddy, x, ldx, mean, rstd,
                                                          gamma, resid_grad, ldr, dx, lddx,

@@ -105,8 +105,10 @@ def layernorm_fwd(x: torch.Tensor, gamma, beta, *, out_dtype=BF16, eps: float = 
 
 
 def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, mean, rstd, gamma, *, resid_grad=None, want_dx=True,
-                  dx_out: Optional[torch.Tensor] = None, want_bf16=False, row_scale=None, rows_per_group=1):
-    """Returns (dx fp32 or None, dx_bf16 or None).  dx = LN'(dy) + resid_grad."""
+                  dx_out: Optional[torch.Tensor] = None, want_bf16=False, row_scale=None, rows_per_group=1,
+                  dgamma: Optional[torch.Tensor] = None, dbeta: Optional[torch.Tensor] = None):
+    """Returns (dx fp32 or None, dx_bf16 or None).  dx = LN'(dy) + resid_grad.  With dgamma/dbeta (fp32 [C]) the
+    parameter gradients are accumulated in the same pass."""
     rows, C = x.shape
     _require_cuda(dy, x)
     dx = dx_out if dx_out is not None else (torch.empty((rows, C), device=x.device, dtype=F32) if want_dx else None)
@@ -117,8 +119,8 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, mean, rstd, gamma, *, resid
                                     + (4 if dx is not None else 0) + (2 if dxb is not None else 0)))
     _lib.call("vsn_layernorm_bwd", _p(dy), dy.stride(0), 1 if dy.dtype == BF16 else 0, _p(x), x.stride(0),
               _p(mean), _p(rstd), _p(gamma), _p(resid_grad), resid_grad.stride(0) if resid_grad is not None else 0,
-              _p(dx), dx.stride(0) if dx is not None else 0, _p(dxb), C, _p(row_scale), rows_per_group, rows, C,
-              _stream())
+              _p(dx), dx.stride(0) if dx is not None else 0, _p(dxb), C, _p(row_scale), rows_per_group,
+              _p(dgamma), _p(dbeta), rows, C, _stream())
     return dx, dxb
 
 

@@ -131,9 +131,8 @@ class SwinBlockFn(torch.autograd.Function):
         ops.colsum(dh, d_fc1_b)
         ops.linear_wgrad(dh, y2, d_fc1_w)
         dy2 = ops.linear_dgrad(dh, w1)
-        ops.ln_param_grad(dy2, x1, mean2, rstd2, d_n2w, d_n2b)
         g1, g1s = ops.layernorm_bwd(dy2, x1, mean2, rstd2, n2w, resid_grad=g, want_bf16=True, row_scale=cfg.scale1,
-                                    rows_per_group=tps)
+                                    rows_per_group=tps, dgamma=d_n2w, dbeta=d_n2b)
         # ---- attention branch: x1 = x + s1 * (Wp attn(Wq LN1(x) + bq) + bp)
         ops.colsum(g1s, d_proj_b)
         ops.linear_wgrad(g1s, o, d_proj_w)
@@ -144,8 +143,7 @@ class SwinBlockFn(torch.autograd.Function):
             ops.colsum(dqkv, d_qkv_b)
         ops.linear_wgrad(dqkv, y1, d_qkv_w)
         dy1 = ops.linear_dgrad(dqkv, wq)
-        ops.ln_param_grad(dy1, x, mean1, rstd1, d_n1w, d_n1b)
-        g0, _ = ops.layernorm_bwd(dy1, x, mean1, rstd1, n1w, resid_grad=g1, dx_out=g1)
+        g0, _ = ops.layernorm_bwd(dy1, x, mean1, rstd1, n1w, resid_grad=g1, dx_out=g1, dgamma=d_n1w, dbeta=d_n1b)
         return (g0, d_n1w, d_n1b, d_qkv_w, d_qkv_b if ctx.has_qkv_bias else None, d_table, d_proj_w, d_proj_b,
                 d_n2w, d_n2b, d_fc1_w, d_fc1_b, d_fc2_w, d_fc2_b, None)
 
@@ -178,8 +176,7 @@ class PatchEmbedFn(torch.autograd.Function):
         if ctx.has_norm:
             rows, y, mean, rstd, nw = ctx.saved_tensors
             d_nw, d_nb = torch.zeros(C, device=dev, dtype=F32), torch.zeros(C, device=dev, dtype=F32)
-            ops.ln_param_grad(g, y, mean, rstd, d_nw, d_nb)
-            _, dyb = ops.layernorm_bwd(g, y, mean, rstd, nw, want_dx=False, want_bf16=True)
+            _, dyb = ops.layernorm_bwd(g, y, mean, rstd, nw, want_dx=False, want_bf16=True, dgamma=d_nw, dbeta=d_nb)
         else:
             (rows,) = ctx.saved_tensors
             d_nw = d_nb = None
@@ -228,8 +225,7 @@ class PatchMergeFn(torch.autograd.Function):
         ops.linear_wgrad(gb, y, d_w)
         dy = ops.linear_dgrad(gb, w16)
         d_nw, d_nb = torch.zeros(8 * C, device=dev, dtype=F32), torch.zeros(8 * C, device=dev, dtype=F32)
-        ops.ln_param_grad(dy, xg, mean, rstd, d_nw, d_nb)
-        dxg, _ = ops.layernorm_bwd(dy, xg, mean, rstd, nw)
+        dxg, _ = ops.layernorm_bwd(dy, xg, mean, rstd, nw, dgamma=d_nw, dbeta=d_nb)
         dx = ops.merge_scatter(dxg, pdims, rdims, B, C)
         return dx, d_nw, d_nb, d_w, None, None, None, None
 
@@ -268,8 +264,7 @@ class NormPoolHeadFn(torch.autograd.Function):
             dfeat = g
         dy = ops.token_mean_bwd(dfeat, B, T, Fd)
         d_nw, d_nb = torch.zeros(Fd, device=dev, dtype=F32), torch.zeros(Fd, device=dev, dtype=F32)
-        ops.ln_param_grad(dy, x, mean, rstd, d_nw, d_nb)
-        dx, _ = ops.layernorm_bwd(dy, x, mean, rstd, nw)
+        dx, _ = ops.layernorm_bwd(dy, x, mean, rstd, nw, dgamma=d_nw, dbeta=d_nb)
         return dx, d_nw, d_nb, d_hw, (d_hb if has_bias else None), None, None
 
 
