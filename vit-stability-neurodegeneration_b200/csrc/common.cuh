@@ -61,6 +61,29 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
 // Exact-erf GELU (nn.GELU default, models/swin_transformer_3d.py:60, models/vit_3d.py:72) and its derivative.
 // erf(z) = 1 - 2^(-z Q(z)) on z in [0,4] with a degree-5 fit of Q (max abs error 3.5e-6 on erf, 2.1e-6 on GELU;
 // clamped at z = 4 where 1 - erf < 2e-8): one MUFU and ~12 FP32 instructions instead of libdevice erff's ~30.
+// 2^x for x <= 0 on the FMA / ALU pipes (Cody-Waite split + degree-4 polynomial, relative error < 5e-5):
+// MUFU.EX2 issues at 16 clk per warp on B200, so kernels that need one exponential per element alternate.
+__device__ __forceinline__ float exp2_neg_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;                 // 1.5 * 2^23: integer part lands in the low mantissa bits
+  const float r = x - (t - 12582912.f);           // r in [-0.5, 0.5]
+  float p = fmaf(r, 0.0096181291f, 0.0555041087f);
+  p = fmaf(p, r, 0.2402265070f);
+  p = fmaf(p, r, 0.6931471806f);
+  p = fmaf(p, r, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+template <bool POLY>
+__device__ __forceinline__ float exp2_neg(float x) {
+  if constexpr (POLY) {
+    return exp2_neg_poly(x);
+  } else {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+  }
+}
+template <bool POLY>
 __device__ __forceinline__ float erfc_half_pos(float ax) {   // 0.5 * erfc(ax / sqrt(2)) for ax >= 0
   const float z = fminf(ax * 0.70710678118654752440f, 4.0f);
   float q = fmaf(z, -0.000233418324f, 0.00402740239f);
@@ -68,20 +91,24 @@ __device__ __forceinline__ float erfc_half_pos(float ax) {   // 0.5 * erfc(ax / 
   q = fmaf(q, z, 0.149565667f);
   q = fmaf(q, z, 0.918361976f);
   q = fmaf(q, z, 1.62790073f);
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * q));
-  return 0.5f * e;
+  return 0.5f * exp2_neg<POLY>(-z * q);
 }
+template <bool POLY = false>
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float t = x * erfc_half_pos(fabsf(x));     // x * (1 - Phi(|x|))
+  const float t = x * erfc_half_pos<POLY>(fabsf(x));     // x * (1 - Phi(|x|))
   return x < 0.f ? t : x - t;
 }
+// The cdf term uses the MUFU or the polynomial exponential (POLY); the pdf term always uses the other one,
+// so every element costs exactly one MUFU.
+template <bool POLY = false>
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float h = erfc_half_pos(fabsf(x));
+  const float h = erfc_half_pos<POLY>(fabsf(x));
   const float cdf = x < 0.f ? h : 1.0f - h;
-  float g;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(x * x * -0.72134752044448170368f));   // exp(-x^2/2)
+  const float g = exp2_neg<!POLY>(x * x * -0.72134752044448170368f);   // exp(-x^2/2)
   return fmaf(x * 0.39894228040143267794f, g, cdf);
 }
+// bf16 values of a packed pair as fp32 (exact)
+__device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 __host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ __forceinline__ long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }

@@ -43,9 +43,9 @@ template <int BN>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (196 * 1024) / STAGE_BYTES > 8 ? 8 : (196 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;   // two accumulator buffers
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias*/;
 };
 
 constexpr int GEMM_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
@@ -64,54 +64,54 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmArgs& p, int tile, in
   return t;
 }
 
-// One 32-column chunk of an output row: v = fp32 accumulators from TMEM.
-__device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, int row, int n, float rs, const uint32_t* v) {
+// One 32-column chunk of an output row: v = fp32 accumulators from TMEM, bias_s = the chunk's bias in smem.
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, int row, int n, float rs, const uint32_t* v,
+                                               const float* bias_s) {
   const int nvalid = min(32, p.N - n);
   float f[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
   if (p.bias != nullptr) {
-    if (nvalid == 32) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 b4 = *reinterpret_cast<const float4*>(p.bias + n + j);
-        f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-      }
-    } else {
-      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { f[j] += p.bias[n + j]; }
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(bias_s + j);   // broadcast read
+      f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
     }
   }
   if (p.act == 1) {
+    // GELU is evaluated on the bf16-rounded pre-activation so backward (which only has the saved bf16
+    // value) differentiates exactly the function forward applied; the rounding reuses the packed pairs.
     bf16* ap = p.aux + static_cast<long long>(row) * p.ldaux + n;
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
     if (nvalid == 32) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        uint4 u;
-        u.x = pack_bf16(f[j], f[j + 1]); u.y = pack_bf16(f[j + 2], f[j + 3]);
-        u.z = pack_bf16(f[j + 4], f[j + 5]); u.w = pack_bf16(f[j + 6], f[j + 7]);
-        *reinterpret_cast<uint4*>(ap + j) = u;
-      }
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(ap + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
     } else {
       _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { ap[j] = __float2bfloat16(f[j]); }
     }
-    // GELU is evaluated on the bf16-rounded pre-activation so backward (which only has the
-    // saved bf16 value) differentiates exactly the function forward applied.
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(__bfloat162float(__float2bfloat16(f[j])));
+    for (int j = 0; j < 16; ++j) {
+      f[2 * j] = gelu_erf<false>(bf16lo(pk[j]));
+      f[2 * j + 1] = gelu_erf<true>(bf16hi(pk[j]));
+    }
   } else if (p.act == 2) {
     const bf16* ap = p.aux + static_cast<long long>(row) * p.ldaux + n;
     if (nvalid == 32) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        const uint4 u = *reinterpret_cast<const uint4*>(ap + j);
-        float2 t;
-        t = unpack_bf16(u.x); f[j] *= gelu_erf_grad(t.x); f[j + 1] *= gelu_erf_grad(t.y);
-        t = unpack_bf16(u.y); f[j + 2] *= gelu_erf_grad(t.x); f[j + 3] *= gelu_erf_grad(t.y);
-        t = unpack_bf16(u.z); f[j + 4] *= gelu_erf_grad(t.x); f[j + 5] *= gelu_erf_grad(t.y);
-        t = unpack_bf16(u.w); f[j + 6] *= gelu_erf_grad(t.x); f[j + 7] *= gelu_erf_grad(t.y);
+      for (int j = 0; j < 4; ++j) {
+        const uint4 u = *reinterpret_cast<const uint4*>(ap + 8 * j);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          f[8 * j + 2 * t] *= gelu_erf_grad<false>(bf16lo(w[t]));
+          f[8 * j + 2 * t + 1] *= gelu_erf_grad<true>(bf16hi(w[t]));
+        }
       }
     } else {
-      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { f[j] *= gelu_erf_grad(__bfloat162float(ap[j])); }
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { f[j] *= gelu_erf_grad<false>(__bfloat162float(ap[j])); }
     }
   }
   if (rs != 1.0f) {
@@ -153,8 +153,16 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, int row, int n
       _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { op[j] = f[j]; }
     }
   } else {
+    // split-K partial sums: vectorised fp32 reductions (red.global.add.v4.f32)
     float* op = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + n;
-    _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { atomicAdd(op + j, f[j]); }
+    if (nvalid == 32 && (reinterpret_cast<uintptr_t>(op) & 15) == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(op + j), "f"(f[j]), "f"(f[j + 1]),
+                     "f"(f[j + 2]), "f"(f[j + 3]) : "memory");
+    } else {
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { atomicAdd(op + j, f[j]); }
+    }
   }
 }
 
@@ -172,6 +180,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   uint64_t* acc_full = empty_bar + C::STAGES;     // [2] MMA commit -> epilogue
   uint64_t* acc_empty = acc_full + 2;             // [2] epilogue threads -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* bias_s = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);   // [2][256]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -261,23 +270,39 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     // ---- epilogue: thread <-> output row; warps 2-5 take the even 32-column chunks, 6-9 the odd ones ----
     const int lg = warp & 3;                     // TMEM lane group this warp may touch
     const int par = (warp - 2) >> 2;             // chunk parity
+    const int et = threadIdx.x - 64;             // 0..255
+    constexpr int NCH = (BN / 32 + 1) / 2;       // chunks per warp (upper bound)
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
       const TileCoord t = decode_tile(p, tile, tiles_n, BN);
       const int buf = lt & 1;
       const int row = t.m0 + lg * 32 + lane;
+      float* bs = bias_s + buf * 256;
+      if (p.bias != nullptr) {
+        // the tile's bias slice goes through smem: one coalesced load per tile instead of 8 dependent
+        // global loads per chunk and thread (the buffer's previous readers finished two tiles ago)
+        if (et < BN) bs[et] = (t.n0 + et < p.N) ? p.bias[t.n0 + et] : 0.f;
+        tc::named_bar_sync(1, EPI_THREADS);
+      }
       tc::mbar_wait(&acc_full[buf], (lt >> 1) & 1);
       tc::fence_after_sync();
       const bool row_ok = row < p.M;
       float rs = p.alpha;
       if (p.row_scale != nullptr && row_ok) rs *= p.row_scale[row / p.rows_per_group];
-#pragma unroll 1
-      for (int c0 = par * 32; c0 < BN; c0 += 64) {
-        uint32_t v[32];
-        tc::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + buf * BN + c0, v);
-        tc::tmem_ld_wait();
-        const int n = t.n0 + c0;
-        if (row_ok && n < p.N) epilogue_chunk(p, row, n, rs, v);
+      const uint32_t tb = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + buf * BN;
+      // software pipeline over this warp's chunks: the TMEM load of chunk i+1 is in flight while chunk i
+      // goes through the epilogue math and stores
+      uint32_t v[2][32];
+      if (par * 32 < BN) tc::tmem_ld_32x32b_x32(tb + par * 32, v[0]);
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int c0 = par * 32 + i * 64;
+        if (c0 < BN) {
+          tc::tmem_ld_wait();
+          if (c0 + 64 < BN) tc::tmem_ld_32x32b_x32(tb + c0 + 64, v[(i + 1) & 1]);
+          const int n = t.n0 + c0;
+          if (row_ok && n < p.N) epilogue_chunk(p, row, n, rs, v[i & 1], bs + c0);
+        }
       }
       tc::fence_before_sync();
       tc::mbar_arrive(&acc_empty[buf]);
