@@ -11,6 +11,7 @@
 // Replaces the cuBLAS calls behind nn.Linear / F.linear in the reference
 // (models/swin_transformer_3d.py:52-69,154-156,550; models/vit_3d.py:59-75,102-105,372).
 #include <cuda.h>
+#include <stdlib.h>
 #include "tc.cuh"
 
 namespace {
@@ -37,6 +38,7 @@ struct GemmArgs {
   const float* row_scale;  // per row-group scale (DropPath keep/(1-p)); null = 1
   int rows_per_group;
   float alpha;
+  int wide;             // 1: out / aux / resid rows are 32-byte aligned -> 256-bit accesses
 };
 
 template <int BN>
@@ -48,8 +50,6 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias*/;
 };
 
-constexpr int GEMM_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
-constexpr int EPI_THREADS = 256;
 
 struct TileCoord { int m0, n0, kb0, nkb; };
 
@@ -85,7 +85,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, int row, int n
     uint32_t pk[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
-    if (nvalid == 32) {
+    if (nvalid == 32 && p.wide) {
+      st_global_v8(ap, pk);
+      st_global_v8(ap + 16, pk + 8);
+    } else if (nvalid == 32) {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         *reinterpret_cast<uint4*>(ap + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
@@ -100,15 +103,21 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, int row, int n
   } else if (p.act == 2) {
     const bf16* ap = p.aux + static_cast<long long>(row) * p.ldaux + n;
     if (nvalid == 32) {
+      uint32_t w[16];
+      if (p.wide) {
+        ld_global_v8(ap, w);
+        ld_global_v8(ap + 16, w + 8);
+      } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint4 u = *reinterpret_cast<const uint4*>(ap + 8 * j);
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          f[8 * j + 2 * t] *= gelu_erf_grad<false>(bf16lo(w[t]));
-          f[8 * j + 2 * t + 1] *= gelu_erf_grad<true>(bf16hi(w[t]));
+        for (int j = 0; j < 4; ++j) {
+          const uint4 u = *reinterpret_cast<const uint4*>(ap + 8 * j);
+          w[4 * j] = u.x; w[4 * j + 1] = u.y; w[4 * j + 2] = u.z; w[4 * j + 3] = u.w;
         }
+      }
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        f[2 * t] *= gelu_erf_grad<false>(bf16lo(w[t]));
+        f[2 * t + 1] *= gelu_erf_grad<true>(bf16hi(w[t]));
       }
     } else {
       _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { f[j] *= gelu_erf_grad<false>(__bfloat162float(ap[j])); }
@@ -120,7 +129,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, int row, int n
   }
   if (p.resid != nullptr) {
     const float* rp = p.resid + static_cast<long long>(row) * p.ldr + n;
-    if (nvalid == 32) {
+    if (nvalid == 32 && p.wide) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint32_t r8[8];
+        ld_global_v8(rp + j, r8);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) f[j + t] += __uint_as_float(r8[t]);
+      }
+    } else if (nvalid == 32) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
@@ -132,7 +149,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, int row, int n
   }
   if (p.out_kind == 0) {
     bf16* op = reinterpret_cast<bf16*>(p.out) + static_cast<long long>(row) * p.ldo + n;
-    if (nvalid == 32) {
+    if (nvalid == 32 && p.wide) {
+      uint32_t o[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
+      st_global_v8(op, o);
+      st_global_v8(op + 16, o + 8);
+    } else if (nvalid == 32) {
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
         uint4 u;
@@ -145,7 +168,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, int row, int n
     }
   } else if (p.out_kind == 1) {
     float* op = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + n;
-    if (nvalid == 32) {
+    if (nvalid == 32 && p.wide) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint32_t o[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) o[t] = __float_as_uint(f[j + t]);
+        st_global_v8(op + j, o);
+      }
+    } else if (nvalid == 32) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
         *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
@@ -168,11 +199,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, int row, int n
 
 // Persistent: CTA b works on tiles b, b + gridDim.x, ...  The TMA ring runs ahead across tile boundaries and the
 // accumulator is double-buffered in TMEM, so the MMAs of tile i+1 overlap the epilogue of tile i.
-template <int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                   const __grid_constant__ CUtensorMap tmB,
-                                                                   const GemmArgs p) {
+// EW = number of epilogue warps (8 or 16).  Small-K problems are bound by the epilogue (one MUFU + ~25 FP32
+// instructions per element for the GELU variants, the stores for the others), so they run 16 epilogue warps
+// (4 per scheduler) to hide latency; large-K problems keep 8 with software-pipelined TMEM loads.
+template <int BN, int EW>
+__global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                  const __grid_constant__ CUtensorMap tmB,
+                                                                  const GemmArgs p) {
   using C = Cfg<BN>;
+  constexpr int EPI_THREADS = EW * 32;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -267,11 +302,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       }
     }
   } else {
-    // ---- epilogue: thread <-> output row; warps 2-5 take the even 32-column chunks, 6-9 the odd ones ----
+    // ---- epilogue: thread <-> output row; epilogue warp e handles the 32-column chunks c = e/4 (mod EW/4) ----
     const int lg = warp & 3;                     // TMEM lane group this warp may touch
-    const int par = (warp - 2) >> 2;             // chunk parity
-    const int et = threadIdx.x - 64;             // 0..255
-    constexpr int NCH = (BN / 32 + 1) / 2;       // chunks per warp (upper bound)
+    constexpr int NPAR = EW / 4;                 // warps per lane group
+    const int par = (warp - 2) >> 2;             // which chunks of the tile
+    const int et = threadIdx.x - 64;
+    constexpr int NCH = (BN / 32 + NPAR - 1) / NPAR;   // chunks per warp (upper bound)
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
       const TileCoord t = decode_tile(p, tile, tiles_n, BN);
@@ -290,18 +326,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       float rs = p.alpha;
       if (p.row_scale != nullptr && row_ok) rs *= p.row_scale[row / p.rows_per_group];
       const uint32_t tb = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + buf * BN;
-      // software pipeline over this warp's chunks: the TMEM load of chunk i+1 is in flight while chunk i
-      // goes through the epilogue math and stores
-      uint32_t v[2][32];
-      if (par * 32 < BN) tc::tmem_ld_32x32b_x32(tb + par * 32, v[0]);
+      if constexpr (EW == 8) {
+        // software pipeline over this warp's chunks: the TMEM load of chunk i+1 is in flight while chunk i
+        // goes through the epilogue math and stores
+        uint32_t v[2][32];
+        if (par * 32 < BN) tc::tmem_ld_32x32b_x32(tb + par * 32, v[0]);
 #pragma unroll
-      for (int i = 0; i < NCH; ++i) {
-        const int c0 = par * 32 + i * 64;
-        if (c0 < BN) {
+        for (int i = 0; i < NCH; ++i) {
+          const int c0 = (par + i * NPAR) * 32;
+          if (c0 < BN) {
+            tc::tmem_ld_wait();
+            if (c0 + NPAR * 32 < BN) tc::tmem_ld_32x32b_x32(tb + c0 + NPAR * 32, v[(i + 1) & 1]);
+            const int n = t.n0 + c0;
+            if (row_ok && n < p.N) epilogue_chunk(p, row, n, rs, v[i & 1], bs + c0);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c0 = par * 32; c0 < BN; c0 += NPAR * 32) {
+          uint32_t v[32];
+          tc::tmem_ld_32x32b_x32(tb + c0, v);
           tc::tmem_ld_wait();
-          if (c0 + 64 < BN) tc::tmem_ld_32x32b_x32(tb + c0 + 64, v[(i + 1) & 1]);
           const int n = t.n0 + c0;
-          if (row_ok && n < p.N) epilogue_chunk(p, row, n, rs, v[i & 1], bs + c0);
+          if (row_ok && n < p.N) epilogue_chunk(p, row, n, rs, v, bs + c0);
         }
       }
       tc::fence_before_sync();
@@ -351,19 +398,26 @@ int make_tmap_2d(CUtensorMap* map, const void* base, long long dim0, long long d
   return 0;
 }
 
-template <int BN>
+template <int BN, int EW>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs a, int splits, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    VSN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+    VSN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
     attr_set = true;
   }
   a.splits = splits;
   a.total_tiles = ceil_div(a.M, BM) * ceil_div(a.N, BN) * splits;
   const int grid = a.total_tiles < vsn_num_sms() ? a.total_tiles : vsn_num_sms();
-  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, a);
+  gemm_tc_kernel<BN, EW><<<grid, 64 + EW * 32, Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, a);
   VSN_LAUNCH_CHECK();
   return 0;
+}
+
+// VSN_GEMM_EW=8|16 overrides the epilogue-warp heuristic (measurements only)
+int forced_ew() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VSN_GEMM_EW"); v = e ? atoi(e) : 0; }
+  return v;
 }
 
 }  // namespace
@@ -383,7 +437,7 @@ extern "C" int vsn_gemm_bf16(const void* A, long long lda, int a_mn, const void*
   int BN;
   if (b_mn) BN = (N % 256 == 0) ? 256 : (N % 192 == 0) ? 192 : (N <= 64) ? 64 : 128;
   else if (N % 256 == 0) BN = 256;
-  else if (N % 192 == 0) BN = 192;
+  else if (N % 192 == 0 && !(K <= 256 && N % 128 == 0)) BN = 192;   // 16 epilogue warps want 4 | BN/32
   else if (N % 128 == 0) BN = 128;
   else if (N % 96 == 0) BN = 96;
   else if (N <= 64) BN = 64;
@@ -419,12 +473,30 @@ extern "C" int vsn_gemm_bf16(const void* A, long long lda, int a_mn, const void*
   a.out = out; a.ldo = ldo; a.out_kind = out_kind; a.bias = bias; a.act = act;
   a.aux = reinterpret_cast<bf16*>(aux); a.ldaux = ldaux; a.resid = resid; a.ldr = ldr;
   a.row_scale = row_scale; a.rows_per_group = rows_per_group > 0 ? rows_per_group : 1; a.alpha = alpha;
+  {
+    const long long osz = out_kind == 0 ? 2 : 4;
+    bool wide = (reinterpret_cast<uintptr_t>(out) % 32 == 0) && ((ldo * osz) % 32 == 0);
+    if (aux != nullptr) wide = wide && (reinterpret_cast<uintptr_t>(aux) % 32 == 0) && ((ldaux * 2) % 32 == 0);
+    if (resid != nullptr) wide = wide && (reinterpret_cast<uintptr_t>(resid) % 32 == 0) && ((ldr * 4) % 32 == 0);
+    a.wide = wide ? 1 : 0;
+  }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int ew = (K <= 256 && out_kind != 2) ? 16 : 8;
+  if (forced_ew() == 8 || forced_ew() == 16) ew = forced_ew();
+  if (ew == 16) {
+    switch (BN) {
+      case 64: return launch<64, 16>(tmA, tmB, a, splits, s);
+      case 96: return launch<96, 16>(tmA, tmB, a, splits, s);
+      case 192: return launch<192, 16>(tmA, tmB, a, splits, s);
+      case 256: return launch<256, 16>(tmA, tmB, a, splits, s);
+      default: return launch<128, 16>(tmA, tmB, a, splits, s);
+    }
+  }
   switch (BN) {
-    case 64: return launch<64>(tmA, tmB, a, splits, s);
-    case 96: return launch<96>(tmA, tmB, a, splits, s);
-    case 192: return launch<192>(tmA, tmB, a, splits, s);
-    case 256: return launch<256>(tmA, tmB, a, splits, s);
-    default: return launch<128>(tmA, tmB, a, splits, s);
+    case 64: return launch<64, 8>(tmA, tmB, a, splits, s);
+    case 96: return launch<96, 8>(tmA, tmB, a, splits, s);
+    case 192: return launch<192, 8>(tmA, tmB, a, splits, s);
+    case 256: return launch<256, 8>(tmA, tmB, a, splits, s);
+    default: return launch<128, 8>(tmA, tmB, a, splits, s);
   }
 }
