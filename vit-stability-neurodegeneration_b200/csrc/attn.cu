@@ -686,6 +686,7 @@ int fill_params(AttnParams& p, int S, int N, int heads, int hd, int win, const i
     VSN_CHECK(S == p.B * p.nWd * p.nWh * p.nWw, "window count mismatch");
     VSN_CHECK(table == nullptr || table_len == (2 * p.wd - 1) * (2 * p.wh - 1) * (2 * p.ww - 1), "bias table length mismatch");
     VSN_CHECK(static_cast<long long>(p.B) * p.Dp * p.Hp * p.Wp < (1LL << 31), "token count overflows int32");
+    VSN_CHECK(p.Dp < 1024 && p.Hp < 1024 && p.Wp < 1024, "stage grid axis exceeds 1023 tokens");
   } else {
     p.B = S; p.Dp = p.Hp = p.Wp = p.wd = p.wh = p.ww = 1; p.sd = p.sh = p.sw = 0; p.nWd = p.nWh = p.nWw = 1; p.use_mask = 0;
   }
@@ -741,19 +742,17 @@ extern "C" int vsn_attn_bwd(const void* qkv, const void* out, const void* dout, 
   p.qkv = reinterpret_cast<const bf16*>(qkv); p.dout = reinterpret_cast<const bf16*>(dout);
   p.lse = const_cast<float*>(lse); p.delta = delta; p.dqkv = reinterpret_cast<bf16*>(dqkv);
   p.dbias_dense = dbias_dense;
-  VSN_CHECK(table == nullptr || (dbias_dense != nullptr && dtable != nullptr), "bias table given without gradient buffers");
+  VSN_CHECK(table == nullptr || dtable != nullptr, "bias table given without its gradient buffer");
+  const bool tc_path = win && wattn_tc_supported(p.wd, p.wh, p.ww, hd) && !vsn_force_legacy_attn();
+  VSN_CHECK(table == nullptr || tc_path || dbias_dense != nullptr, "the mma.sync path needs the dense bias-gradient scratch");
   if (S == 0) return 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bf16* o = reinterpret_cast<const bf16*>(out);
   if (win && wattn_tc_supported(p.wd, p.wh, p.ww, hd) && !vsn_force_legacy_attn()) {
     p.out = const_cast<bf16*>(o);
-    if (int rc = wattn_tc_bwd(to_tc_args(p), delta, st)) return rc;
-    if (table != nullptr) {
-      const int n = table_len * heads;
-      bias_table_grad_kernel<<<ceil_div(n, 128), 128, 0, st>>>(dbias_dense, dtable, heads, N, p.Npad, p.wd, p.wh, p.ww, table_len, 1);
-      VSN_LAUNCH_CHECK();
-    }
-    return 0;
+    WinAttnArgs ta = to_tc_args(p);
+    ta.dtable = table != nullptr ? dtable : nullptr;
+    return wattn_tc_bwd(ta, delta, st);
   }
   if (win) attn_delta_kernel<true><<<S, 128, 0, st>>>(p, o, delta);
   else attn_delta_kernel<false><<<S, 128, 0, st>>>(p, o, delta);

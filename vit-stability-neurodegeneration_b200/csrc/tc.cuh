@@ -203,6 +203,24 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t saddr, uint32_t
   return d;
 }
 
+// True in exactly one lane of a fully converged warp.  The MMA-issuing warp runs its whole control flow
+// converged (all lanes wait on the mbarriers) and only the tcgen05.mma / tcgen05.commit sit under this
+// predicate: the operands stay warp-uniform, so the compiler does not wrap each issue in a divergence loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// Descriptor for (base address + byte offset): the address field holds addr >> 4 in the low 14 bits and smem
+// addresses are < 256 KB, so advancing a descriptor is one 64-bit add.
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t byte_offset) { return desc + (byte_offset >> 4); }
+
 // ---- UMMA descriptors (layout per cute/arch/mma_sm100_desc.hpp) ---------------------
 // Shared-memory matrix descriptor, 128-byte swizzle, sm_100 version bit set.
 //   K-major  operand: rows of 64 bf16 (128 B), 8-row atoms of 1024 B: LBO unused(1), SBO = 1024 B.

@@ -100,24 +100,43 @@ struct BiasTab {
   }
 };
 
-template <int WD, int WH, int WW>
-__device__ __forceinline__ TokenGeom token_geom_t(const WinAttnArgs& p, int s, int i) {
+// Per-window part of the geometry (three runtime integer divisions): computed once per window, not per tile.
+struct WinCoord {
+  int bm;     // batch index << 1 | masked (the window straddles a region boundary: last along a shifted axis)
+  int dhw;    // origin of the window on the rolled (shifted) grid, 10 bits per axis
+  __device__ __forceinline__ bool masked() const { return bm & 1; }
+};
+__device__ __forceinline__ WinCoord win_coord(const WinAttnArgs& p, int s, int wd, int wh, int ww) {
   const int nW = p.nWd * p.nWh * p.nWw;
   const int b = s / nW, wi = s - b * nW;
   const int wa = wi / (p.nWh * p.nWw), wr = wi - wa * (p.nWh * p.nWw), wb = wr / p.nWw, wc = wr - wb * p.nWw;
+  const bool masked = p.use_mask && ((p.sd > 0 && wa == p.nWd - 1) || (p.sh > 0 && wb == p.nWh - 1) || (p.sw > 0 && wc == p.nWw - 1));
+  WinCoord c;
+  c.bm = (b << 1) | (masked ? 1 : 0);
+  c.dhw = ((wa * wd) << 20) | ((wb * wh) << 10) | (wc * ww);
+  return c;
+}
+// token i of the window (window_partition order) -> source row after the cyclic shift and region code
+// (models/swin_transformer_3d.py:333-341,463-492); only divisions by compile-time constants
+template <int WD, int WH, int WW>
+__device__ __forceinline__ TokenGeom token_geom_w(const WinAttnArgs& p, const WinCoord& c, int i) {
   const int ld = i / (WH * WW), lr = i - ld * (WH * WW), lh = lr / WW, lw = lr - lh * WW;
-  const int dd = wa * WD + ld, hh = wb * WH + lh, wv = wc * WW + lw;
+  const int dd = (c.dhw >> 20) + ld, hh = ((c.dhw >> 10) & 1023) + lh, wv = (c.dhw & 1023) + lw;
   int d0 = dd + p.sd; if (d0 >= p.Dp) d0 -= p.Dp;
   int h0 = hh + p.sh; if (h0 >= p.Hp) h0 -= p.Hp;
   int w0 = wv + p.sw; if (w0 >= p.Wp) w0 -= p.Wp;
   TokenGeom g;
-  g.row = ((b * p.Dp + d0) * p.Hp + h0) * p.Wp + w0;
+  g.row = (((c.bm >> 1) * p.Dp + d0) * p.Hp + h0) * p.Wp + w0;
   const int rd = dd < p.Dp - WD ? 0 : (dd < p.Dp - p.sd ? 1 : 2);
   const int rh = hh < p.Hp - WH ? 0 : (hh < p.Hp - p.sh ? 1 : 2);
   const int rw = wv < p.Wp - WW ? 0 : (wv < p.Wp - p.sw ? 1 : 2);
   g.code = 9 * rd + 3 * rh + rw;
   g.lin = 0;
   return g;
+}
+template <int WD, int WH, int WW>
+__device__ __forceinline__ TokenGeom token_geom_t(const WinAttnArgs& p, int s, int i) {
+  return token_geom_w<WD, WH, WW>(p, win_coord(p, s, WD, WH, WW), i);
 }
 
 // =========================================== forward ==============================================
@@ -233,8 +252,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
       const int st = it & 1;
       tc::mbar_wait_relaxed(&qkv_empty[st], ((it >> 1) & 1) ^ 1);
       uint8_t* sq = stages + st * STAGE_BYTES;
+      const WinCoord wc = win_coord(p, s, WD, WH, WW);
       for (int i = lane; i < N; i += 32) {
-        const TokenGeom g = token_geom_t<WD, WH, WW>(p, s, i);
+        const TokenGeom g = token_geom_w<WD, WH, WW>(p, wc, i);
         keycode[st * NP + i] = static_cast<uint8_t>(g.code);
         const bf16* src = p.qkv + g.row * ld + head * HD;
 #pragma unroll
@@ -250,36 +270,43 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
       tc::mbar_arrive(&qkv_full[st]);
     }
   } else if (warp == SM_WARPS + 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (warp runs converged)
+    {
       const uint32_t idesc_s = tc::make_idesc_bf16(128, NP, 0, 0);
       const uint32_t idesc_o = tc::make_idesc_bf16(128, HD, 0, 1);
+      const uint64_t desc_st0 = tc::make_smem_desc_sw64(tc::smem_u32(stages), 16, 512);
       for (int u = 0; u <= U; ++u) {
         if (u < U) {
           const int it = u >> 1, h = u & 1, st = it & 1;
           if (h == 0) tc::mbar_wait(&qkv_full[st], (it >> 1) & 1);
           tc::mbar_wait(&o_read[h], ((u >> 1) & 1) ^ 1);
           tc::fence_after_sync();
-          const uint32_t sq = tc::smem_u32(stages + st * STAGE_BYTES) + h * (128 * 64);
-          const uint32_t sk = tc::smem_u32(stages + st * STAGE_BYTES + TILE_BYTES);
+          const uint64_t dq = tc::desc_advance(desc_st0, st * STAGE_BYTES + h * (128 * 64));
+          const uint64_t dk = tc::desc_advance(desc_st0, st * STAGE_BYTES + TILE_BYTES);
+          if (tc::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k)
-            tc::mma_bf16_ss(tmem_base + h * NP, tc::make_smem_desc_sw64(sq + k * 32, 16, 512),
-                            tc::make_smem_desc_sw64(sk + k * 32, 16, 512), idesc_s, k > 0 ? 1u : 0u);
-          tc::mma_commit(&s_full[h]);
+            for (int k = 0; k < HD / 16; ++k)
+              tc::mma_bf16_ss(tmem_base + h * NP, tc::desc_advance(dq, k * 32), tc::desc_advance(dk, k * 32), idesc_s,
+                              k > 0 ? 1u : 0u);
+            tc::mma_commit(&s_full[h]);
+          }
+          __syncwarp();
         }
         if (u >= 1) {
           const int v = u - 1, it = v >> 1, h = v & 1, st = it & 1;
           tc::mbar_wait(&p_ready[h], (v >> 1) & 1);
           tc::fence_after_sync();
-          const uint32_t sv = tc::smem_u32(stages + st * STAGE_BYTES + 2 * TILE_BYTES);
-          // keys 64*part .. 64*part+63 were exponentiated against their own local max: one accumulator each
+          const uint64_t dv = tc::desc_advance(desc_st0, st * STAGE_BYTES + 2 * TILE_BYTES);
+          if (tc::elect_one()) {
+            // keys 64*part .. 64*part+63 were exponentiated against their own local max: one accumulator each
 #pragma unroll
-          for (int k = 0; k < NP / 16; ++k)
-            tc::mma_bf16_ts(tmem_base + h * NP + 128 + (k >> 2) * 32, tmem_base + h * NP + k * 8,
-                            tc::make_smem_desc_sw64(sv + k * 1024, 16, 512), idesc_o, (k & 3) ? 1u : 0u);
-          tc::mma_commit(&o_full[h]);
-          if (h == 1) tc::mma_commit(&qkv_empty[st]);
+            for (int k = 0; k < NP / 16; ++k)
+              tc::mma_bf16_ts(tmem_base + h * NP + 128 + (k >> 2) * 32, tmem_base + h * NP + k * 8,
+                              tc::desc_advance(dv, k * 1024), idesc_o, (k & 3) ? 1u : 0u);
+            tc::mma_commit(&o_full[h]);
+            if (h == 1) tc::mma_commit(&qkv_empty[st]);
+          }
+          __syncwarp();
         }
       }
     }
@@ -292,6 +319,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
     const int rl = q4 * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q4 * 32) << 16;
     const float cscale = p.scale * LOG2E;
+    WinCoord wc_cur = {}, wc_prev = {};     // window of the current unit / of the unit whose epilogue is pending
 
     auto epilogue = [&](int v) {
       const int h = v & 1;
@@ -331,7 +359,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
       tc::fence_before_sync();
       tc::mbar_arrive(&o_read[h]);
       if (i < N) {
-        const TokenGeom g = token_geom_t<WD, WH, WW>(p, s, i);
+        const TokenGeom g = token_geom_w<WD, WH, WW>(p, wc_prev, i);
         uint4 w;
         w.x = pack_bf16(r[0], r[1]); w.y = pack_bf16(r[2], r[3]); w.z = pack_bf16(r[4], r[5]); w.w = pack_bf16(r[6], r[7]);
         *reinterpret_cast<uint4*>(p.out + static_cast<long long>(g.row) * p.C + head * HD + part * 8) = w;
@@ -346,6 +374,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
       const int i = h * 128 + rl;
       const int ib = i < N ? i : N - 1;
       const int rowbase = BT::rowbase(ib);
+      if (h == 0) wc_cur = win_coord(p, s, WD, WH, WW);     // once per window
 
       tc::mbar_wait(&s_full[h], (u >> 1) & 1);
       tc::fence_after_sync();
@@ -360,8 +389,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
         case 2: add_bias<WD, WH, WW, 2>(x, bias_s, rowbase, cscale); break;
         default: add_bias<WD, WH, WW, 3>(x, bias_s, rowbase, cscale); break;
       }
-      if (window_masked(p, s)) {
-        const uint32_t cq4 = static_cast<uint32_t>(token_geom_t<WD, WH, WW>(p, s, ib).code) * 0x01010101u;
+      if (wc_cur.masked()) {
+        const uint32_t cq4 = static_cast<uint32_t>(token_geom_w<WD, WH, WW>(p, wc_cur, ib).code) * 0x01010101u;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const uint4 kc = *reinterpret_cast<const uint4*>(keycode + st * NP + part * 64 + c * 16);
@@ -392,7 +421,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
       for (int k = 0; k < 32; k += 2) {
         // the epilogue of the previous unit sits in the middle of the exponentials: by then its O is ready
         // and only half of the logits are still live in registers
-        if (k == 16 && u > 0) epilogue(u - 1);
+        if (k == 16 && u > 0) epilogue(u - 1);     // wc_prev = window of unit u-1
         // VAR&1: 1 of 4 exponentials on the FMA pipe instead of the MUFU pipe
         const float p0 = (VAR & 2) ? (__uint_as_float(x[2 * k]) - m) : tc::ex2_approx(__uint_as_float(x[2 * k]) - m);
         const float p1 = (VAR & 2) ? (__uint_as_float(x[2 * k + 1]) - m) : (VAR & 1) ? exp2_poly(__uint_as_float(x[2 * k + 1]) - m) : tc::ex2_approx(__uint_as_float(x[2 * k + 1]) - m);
@@ -409,6 +438,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
       tc::tmem_st_wait();
       tc::fence_before_sync();
       tc::mbar_arrive(&p_ready[h]);
+      wc_prev = wc_cur;
     }
     if (U > 0) epilogue(U - 1);
   }
@@ -526,9 +556,14 @@ __device__ __forceinline__ void add_bias_t16(float* x, const uint8_t* tab, int r
   }
 }
 
-__device__ __forceinline__ void red_add_bf16x2(bf16* addr, uint32_t v) {
-  asm volatile("red.global.add.noftz.bf16x2 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+// 8 bf16 (16 bytes) added to global memory with one REDG.BF16x8
+__device__ __forceinline__ void red_add_bf16x8(bf16* addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
 }
+
+__device__ unsigned long long* g_bwd_timing = nullptr;   // [gridDim][16] cycle counters (VSN_WATTN_TIMING=1)
+#define TCLK() clock64()
 
 template <int WD, int WH, int WW>
 __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttnArgs p, const float* __restrict__ delta_g) {
@@ -545,9 +580,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
   uint64_t* s_full = bars + 4;       // [2 buffers] MMA commit -> compute group
   uint64_t* p_ready = bars + 6;      // [2 buffers] compute group -> MMA
   uint64_t* ds_free = bars + 8;      // [2 query blocks] MMA commit (dQ block done) -> compute threads (smem tile half)
-  uint64_t* unit_done = bars + 10;   // MMA commit: dK, dV, dQ of the window complete -> group 1
-  uint64_t* acc_read = bars + 11;    // group 1: accumulators read out -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* unit_done = bars + 10;   // MMA commit: every MMA of the window (incl. dQ) complete -> group 1
+  uint64_t* acc_read = bars + 11;    // group 1: dV / dK accumulators read out -> MMA (next window's first dV/dK MMA)
+  uint64_t* kv_done = bars + 12;     // MMA commit: dV, dK of the window complete -> group 1
+  uint64_t* dq_read = bars + 13;     // group 1: dQ accumulator read out -> MMA (next window's first dQ MMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.y, kh = blockIdx.z;
@@ -572,6 +609,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
     }
     tc::mbar_init(unit_done, 1);
     tc::mbar_init(acc_read, 256);
+    tc::mbar_init(kv_done, 1);
+    tc::mbar_init(dq_read, 256);
     tc::fence_barrier_init();
   }
   if (warp == 17) tc::tmem_alloc(tmem_slot, 512);
@@ -601,8 +640,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
       const int st = n & 1;
       tc::mbar_wait_relaxed(&ld_empty[st], ((n >> 1) & 1) ^ 1);
       uint8_t* sb = stages + st * BWD_STAGE_BYTES;
+      const WinCoord wc = win_coord(p, s, WD, WH, WW);
       for (int i = lane; i < N; i += 32) {
-        const TokenGeom g = token_geom_t<WD, WH, WW>(p, s, i);
+        const TokenGeom g = token_geom_w<WD, WH, WW>(p, wc, i);
         sb[51200 + i] = static_cast<uint8_t>(g.code);
         const bf16* src = p.qkv + g.row * ld + head * HD;
         const bf16* dsrc = p.dout + static_cast<long long>(g.row) * p.C + head * HD;
@@ -630,62 +670,81 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
       tc::mbar_arrive(&ld_full[st]);
     }
   } else if (warp == 17) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (warp runs converged)
+    {
       const uint32_t idesc_s = tc::make_idesc_bf16(128, QS, 0, 0);     // S^T, dP^T: A K-major, B K-major
       const uint32_t idesc_kv = tc::make_idesc_bf16(128, HD, 0, 1);    // dV, dK: A TMEM, B MN-major
       const uint32_t idesc_b = tc::make_idesc_bf16(128, 16, 0, 0);     // dBias: A TMEM, B = I16
       const uint32_t idesc_q = tc::make_idesc_bf16(128, HD, 1, 1);     // dQ: A MN-major smem, B MN-major
-      const uint64_t idesc_ident = tc::make_smem_desc_sw64(tc::smem_u32(ident), 16, 512);
+      const uint64_t desc_ident = tc::make_smem_desc_sw64(tc::smem_u32(ident), 16, 512);
+      const uint64_t desc_ds = tc::make_smem_desc_sw128(tc::smem_u32(ds_tile), 16384, 1024);
+      const uint64_t desc_st0 = tc::make_smem_desc_sw64(tc::smem_u32(stages), 16, 512);   // stage 0, offset 0
+      long long tm_ld = 0, tm_pr = 0, tm_acc = 0, tm_t0 = TCLK(), tq;
       for (int T = 0; T <= TT; ++T) {
         if (T < TT) {
           const int n = T / NSUB, t = T % NSUB, st = n & 1, b = T & 1;
+          tq = TCLK();
           if (t == 0) tc::mbar_wait(&ld_full[st], (n >> 1) & 1);
+          tm_ld += TCLK() - tq;
           tc::fence_after_sync();
-          const uint32_t sb = tc::smem_u32(stages + st * BWD_STAGE_BYTES);
+          const uint64_t dst = tc::desc_advance(desc_st0, st * BWD_STAGE_BYTES);
           const uint32_t d = tmem_base + COL_BUF + b * 64;
+          if (tc::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 2; ++k)
-            tc::mma_bf16_ss(d, tc::make_smem_desc_sw64(sb + 32768 + k * 32, 16, 512),
-                            tc::make_smem_desc_sw64(sb + t * (QS * 64) + k * 32, 16, 512), idesc_s, k);
+            for (int k = 0; k < 2; ++k)
+              tc::mma_bf16_ss(d, tc::desc_advance(dst, 32768 + k * 32), tc::desc_advance(dst, t * (QS * 64) + k * 32),
+                              idesc_s, k);
 #pragma unroll
-          for (int k = 0; k < 2; ++k)
-            tc::mma_bf16_ss(d + 32, tc::make_smem_desc_sw64(sb + 40960 + k * 32, 16, 512),
-                            tc::make_smem_desc_sw64(sb + 16384 + t * (QS * 64) + k * 32, 16, 512), idesc_s, k);
-          tc::mma_commit(&s_full[b]);
+            for (int k = 0; k < 2; ++k)
+              tc::mma_bf16_ss(d + 32, tc::desc_advance(dst, 40960 + k * 32),
+                              tc::desc_advance(dst, 16384 + t * (QS * 64) + k * 32), idesc_s, k);
+            tc::mma_commit(&s_full[b]);
+          }
+          __syncwarp();
         }
         if (T >= 1) {
           const int V = T - 1, n = V / NSUB, t = V % NSUB, st = n & 1, b = V & 1;
+          tq = TCLK();
           tc::mbar_wait(&p_ready[b], (V >> 1) & 1);
-          if (t == 0) tc::mbar_wait(acc_read, (n & 1) ^ 1);       // previous window's dK/dV/dQ were read out
+          tm_pr += TCLK() - tq;
+          tq = TCLK();
+          if (t == 0) tc::mbar_wait(acc_read, (n & 1) ^ 1);       // previous window's dK / dV were read out
+          if (t == 3) tc::mbar_wait(dq_read, (n & 1) ^ 1);        // previous window's dQ was read out
+          tm_acc += TCLK() - tq;
           tc::fence_after_sync();
-          const uint32_t sb = tc::smem_u32(stages + st * BWD_STAGE_BYTES);
+          const uint64_t dst = tc::desc_advance(desc_st0, st * BWD_STAGE_BYTES);
           const uint32_t a_p = tmem_base + COL_BUF + b * 64;        // P^T  (bf16 pairs: 8 columns per 16 queries, at 16*half)
           const uint32_t a_ds = a_p + 32;                           // dS^T
+          if (tc::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            const uint32_t rows = (t * QS + k * 16) * 64;
-            tc::mma_bf16_ts(tmem_base + COL_DV, a_p + k * 16, tc::make_smem_desc_sw64(sb + 16384 + rows, 16, 512),
-                            idesc_kv, (t | k) ? 1u : 0u);
-            tc::mma_bf16_ts(tmem_base + COL_DK, a_ds + k * 16, tc::make_smem_desc_sw64(sb + rows, 16, 512),
-                            idesc_kv, (t | k) ? 1u : 0u);
-            tc::mma_bf16_ts(tmem_base + t * QS + k * 16, a_ds + k * 16, idesc_ident, idesc_b, n ? 1u : 0u);
-          }
-          if ((t & 3) == 3) {
-            // dQ for the 128-query block that is now complete in the smem tile
-            const int mb = t >> 2;
-            const uint32_t at = tc::smem_u32(ds_tile) + mb * 32768;
+            for (int k = 0; k < 2; ++k) {
+              const uint32_t rows = (t * QS + k * 16) * 64;
+              tc::mma_bf16_ts(tmem_base + COL_DV, a_p + k * 16, tc::desc_advance(dst, 16384 + rows), idesc_kv,
+                              (t | k) ? 1u : 0u);
+              tc::mma_bf16_ts(tmem_base + COL_DK, a_ds + k * 16, tc::desc_advance(dst, rows), idesc_kv, (t | k) ? 1u : 0u);
+              tc::mma_bf16_ts(tmem_base + t * QS + k * 16, a_ds + k * 16, desc_ident, idesc_b, n ? 1u : 0u);
+            }
+            if (t == NSUB - 1) tc::mma_commit(kv_done);
+            if ((t & 3) == 3) {
+              // dQ for the 128-query block that is now complete in the smem tile
+              const int mb = t >> 2;
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-              tc::mma_bf16_ss(tmem_base + COL_DQ + mb * 32, tc::make_smem_desc_sw128(at + k * 2048, 16384, 1024),
-                              tc::make_smem_desc_sw64(sb + 32768 + k * 1024, 16, 512), idesc_q, k);
-            tc::mma_commit(&ds_free[mb]);
-            if (mb == 1) {
-              tc::mma_commit(unit_done);
-              tc::mma_commit(&ld_empty[st]);
+              for (int k = 0; k < 8; ++k)
+                tc::mma_bf16_ss(tmem_base + COL_DQ + mb * 32, tc::desc_advance(desc_ds, mb * 32768 + k * 2048),
+                                tc::desc_advance(dst, 32768 + k * 1024), idesc_q, k);
+              tc::mma_commit(&ds_free[mb]);
+              if (mb == 1) {
+                tc::mma_commit(unit_done);
+                tc::mma_commit(&ld_empty[st]);
+              }
             }
           }
+          __syncwarp();
         }
+      }
+      if (g_bwd_timing != nullptr && lane == 0) {
+        unsigned long long* o = g_bwd_timing + ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16;
+        o[0] = TCLK() - tm_t0; o[1] = tm_ld; o[2] = tm_pr; o[3] = tm_acc; o[4] = TT;
       }
     }
   } else {
@@ -703,15 +762,73 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
     }
     // smem dS tile: element (query q, key r) at (q/64)*16384 + (r/8)*1024 + (r%8)*128 + (((q%64)/8) ^ (r%8))*16
     const uint32_t ds_row = (r >> 3) * 1024 + (r & 7) * 128;
+    WinCoord wc = {};
+    uint32_t ck4 = 0;
+    long long tc_wait = 0, tc_ld = 0, tc_math = 0, tc_st = 0, tc_ro = 0, tc_q;
+    WinCoord wc_prev = {};
+
+    // Read-out of window rn (group 1 only), run one sub-tile into the NEXT window so that kv_done / unit_done have
+    // long fired and nothing here waits.
+    auto readout = [&](int rn, const WinCoord& rwc) {
+        // ---- window read-out.  dV / dK rows of this key half: direct stores, released as soon as they are in
+        // registers (the next window's first MMA overwrites them); dQ partial: bf16 red.add (REDG.BF16x8) into the
+        // zeroed Q block, needed back only at the next window's 4th sub-tile.
+        uint32_t acc[32];
+        tc::mbar_wait(kv_done, rn & 1);
+        tc::fence_after_sync();
+        tc::tmem_ld_32x32b_x32(tmem_base + lane_addr + (half ? COL_DK : COL_DV), acc);
+        tc::tmem_ld_wait();
+        tc::fence_before_sync();
+        tc::mbar_arrive(acc_read);
+        if (j < N) {
+          const TokenGeom gk = token_geom_w<WD, WH, WW>(p, rwc, j);
+          const float sc = half ? p.scale : 1.f;
+          bf16* dst = p.dqkv + static_cast<long long>(gk.row) * (3LL * p.C) + (half ? p.C : 2 * p.C) + head * HD;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint4 w;
+            w.x = pack_bf16(__uint_as_float(acc[8 * c]) * sc, __uint_as_float(acc[8 * c + 1]) * sc);
+            w.y = pack_bf16(__uint_as_float(acc[8 * c + 2]) * sc, __uint_as_float(acc[8 * c + 3]) * sc);
+            w.z = pack_bf16(__uint_as_float(acc[8 * c + 4]) * sc, __uint_as_float(acc[8 * c + 5]) * sc);
+            w.w = pack_bf16(__uint_as_float(acc[8 * c + 6]) * sc, __uint_as_float(acc[8 * c + 7]) * sc);
+            reinterpret_cast<uint4*>(dst)[c] = w;
+          }
+        }
+        const int qi = half * 128 + r;      // query row of the dQ block this thread reads
+        tc::mbar_wait(unit_done, rn & 1);
+        tc::fence_after_sync();
+        tc::tmem_ld_32x32b_x32(tmem_base + lane_addr + COL_DQ + half * 32, acc);
+        tc::tmem_ld_wait();
+        tc::fence_before_sync();
+        tc::mbar_arrive(dq_read);
+        if (qi < N) {
+          const TokenGeom gq = token_geom_w<WD, WH, WW>(p, rwc, qi);
+          bf16* dst = p.dqkv + static_cast<long long>(gq.row) * (3LL * p.C) + head * HD;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            red_add_bf16x8(dst + 8 * c,
+                           pack_bf16(__uint_as_float(acc[8 * c]) * p.scale, __uint_as_float(acc[8 * c + 1]) * p.scale),
+                           pack_bf16(__uint_as_float(acc[8 * c + 2]) * p.scale, __uint_as_float(acc[8 * c + 3]) * p.scale),
+                           pack_bf16(__uint_as_float(acc[8 * c + 4]) * p.scale, __uint_as_float(acc[8 * c + 5]) * p.scale),
+                           pack_bf16(__uint_as_float(acc[8 * c + 6]) * p.scale, __uint_as_float(acc[8 * c + 7]) * p.scale));
+        }
+    };
 
     for (int T = g; T < TT; T += 2) {
       const int n = T / NSUB, t = T % NSUB, st = n & 1;
       const int s = blockIdx.x + n * gridDim.x;
+      if (t < 2) {                                   // first sub-tile of this group in the window
+        wc_prev = wc;
+        wc = win_coord(p, s, WD, WH, WW);
+        ck4 = static_cast<uint32_t>(token_geom_w<WD, WH, WW>(p, wc, jb).code) * 0x01010101u;
+      }
       const uint8_t* sb = stages + st * BWD_STAGE_BYTES;
       const int q0 = t * QS + half * 16;
 
+      tc_q = TCLK();
       tc::mbar_wait(&s_full[g], (T >> 1) & 1);
       tc::fence_after_sync();
+      tc_wait += TCLK() - tc_q; tc_q = TCLK();
       float x[16], dp[16];
       {
         uint32_t u0[16], u1[16];
@@ -722,14 +839,14 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
 #pragma unroll
         for (int k = 0; k < 16; ++k) { x[k] = __uint_as_float(u0[k]); dp[k] = __uint_as_float(u1[k]); }
       }
+      tc_ld += TCLK() - tc_q; tc_q = TCLK();
       const int qr0 = q0 / WW;
       switch (q0 % WW) {
         case 0: add_bias_t16<WD, WH, WW, 0>(x, bias_s, rowbaseT, qr0, cscale); break;
         case 2: add_bias_t16<WD, WH, WW, 2>(x, bias_s, rowbaseT, qr0, cscale); break;
         default: add_bias_t16<WD, WH, WW, 4>(x, bias_s, rowbaseT, qr0, cscale); break;
       }
-      if (window_masked(p, s)) {
-        const uint32_t ck4 = static_cast<uint32_t>(token_geom_t<WD, WH, WW>(p, s, jb).code) * 0x01010101u;
+      if (wc.masked()) {
         const uint4 qc = *reinterpret_cast<const uint4*>(sb + 51200 + q0);
         const uint32_t qw[4] = {qc.x, qc.y, qc.z, qc.w};
 #pragma unroll
@@ -757,6 +874,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
           dk[2 * c + 1] = pack_bf16(p2 * (dp[4 * c + 2] - dl.z), p3 * (dp[4 * c + 3] - dl.w));
         }
       }
+      tc_math += TCLK() - tc_q; tc_q = TCLK();
       // P^T / dS^T over the first 8 of this thread's own 16 columns (bf16 pairs): TMEM A operands
       const uint32_t pb = tmem_base + lane_addr + COL_BUF + g * 64 + half * 16;
       tc::tmem_st_32x32b_x8(pb, pk);
@@ -773,60 +891,55 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
       tc::tmem_st_wait();
       tc::fence_before_sync();
       tc::mbar_arrive(&p_ready[g]);
+      tc_st += TCLK() - tc_q; tc_q = TCLK();
 
-      if (g == 1 && t == NSUB - 1) {
-        // ---- window read-out: dV / dK rows of this key half (direct stores), dQ partial (bf16x2 red.add)
-        tc::mbar_wait(unit_done, n & 1);
-        tc::fence_after_sync();
-        {
-          uint32_t acc[32];
-          tc::tmem_ld_32x32b_x32(tmem_base + lane_addr + (half ? COL_DK : COL_DV), acc);
-          tc::tmem_ld_wait();
-          if (j < N) {
-            const TokenGeom gk = token_geom_t<WD, WH, WW>(p, s, j);
-            const float sc = half ? p.scale : 1.f;
-            bf16* dst = p.dqkv + static_cast<long long>(gk.row) * (3LL * p.C) + (half ? p.C : 2 * p.C) + head * HD;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint4 w;
-              w.x = pack_bf16(__uint_as_float(acc[8 * c]) * sc, __uint_as_float(acc[8 * c + 1]) * sc);
-              w.y = pack_bf16(__uint_as_float(acc[8 * c + 2]) * sc, __uint_as_float(acc[8 * c + 3]) * sc);
-              w.z = pack_bf16(__uint_as_float(acc[8 * c + 4]) * sc, __uint_as_float(acc[8 * c + 5]) * sc);
-              w.w = pack_bf16(__uint_as_float(acc[8 * c + 6]) * sc, __uint_as_float(acc[8 * c + 7]) * sc);
-              reinterpret_cast<uint4*>(dst)[c] = w;
-            }
-          }
-          const int qi = half * 128 + r;      // query row of the dQ block this thread reads
-          tc::tmem_ld_32x32b_x32(tmem_base + lane_addr + COL_DQ + half * 32, acc);
-          tc::tmem_ld_wait();
-          tc::fence_before_sync();
-          tc::mbar_arrive(acc_read);
-          if (qi < N) {
-            const TokenGeom gq = token_geom_t<WD, WH, WW>(p, s, qi);
-            bf16* dst = p.dqkv + static_cast<long long>(gq.row) * (3LL * p.C) + head * HD;
-#pragma unroll
-            for (int c = 0; c < 16; ++c)
-              red_add_bf16x2(dst + 2 * c, pack_bf16(__uint_as_float(acc[2 * c]) * p.scale, __uint_as_float(acc[2 * c + 1]) * p.scale));
-          }
-        }
+      if (g == 1 && t == 1 && n > 0) {
+        readout(n - 1, wc_prev);
+        tc_ro += TCLK() - tc_q;
       }
     }
-    // ---- CTA end: flush the dense bias gradient of this (head, key half): dbias_dense[head][key][query]
-    if (p.dbias_dense != nullptr && TT > 0) {
-      // all MMAs of the CTA are complete once the last unit_done has fired (group 1 waited for it; group 0 waits here)
-      if (g == 0) tc::mbar_wait(unit_done, (n_units - 1) & 1);
+    if (g == 1 && n_units > 0) readout(n_units - 1, wc);
+    if (g_bwd_timing != nullptr && lane == 0 && q4 == 0 && half == 0) {
+      unsigned long long* o = g_bwd_timing + ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + 5 + g * 5;
+      o[0] = tc_wait; o[1] = tc_ld; o[2] = tc_math; o[3] = tc_st; o[4] = tc_ro;
+    }
+    // ---- CTA end: fold this CTA's dense bias gradient [128 keys x 256 queries] (TMEM) onto the
+    // relative_position_bias_table: dT[rpi(i,j)] += dB[j][i], rpi(i,j) = lin(i) - lin(j) + off
+    // (models/swin_transformer_3d.py:132-152,186-190).  Shared-memory fp32 atomics into a 1573-entry table, then
+    // one global atomic per table entry and CTA -- instead of 32768 global atomics plus a separate reduction.
+    if (p.dtable != nullptr && TT > 0) {
+      constexpr int TL = (2 * WD - 1) * (2 * WH - 1) * (2 * WW - 1);
+      constexpr int OFF = (WD - 1) * (2 * WH - 1) * (2 * WW - 1) + (WH - 1) * (2 * WW - 1) + (WW - 1);
+      float* tab_s = reinterpret_cast<float*>(ds_tile);            // the dS tile is free now
+      short* lin_s = reinterpret_cast<short*>(ds_tile + 8192);
+      const int ct = threadIdx.x;                                   // 0..511 (compute threads)
+      // all MMAs of the CTA are complete once the last unit_done has fired
+      tc::mbar_wait(unit_done, (n_units - 1) & 1);
       tc::fence_after_sync();
-      float* dst = p.dbias_dense + (static_cast<long long>(head) * NP + jb) * NP + (g * 2 + half) * 64;
+      for (int e = ct; e < TL; e += 512) tab_s[e] = 0.f;
+      if (ct < NP) {
+        const int ii = ct < N ? ct : N - 1;
+        const int di = ii / (WH * WW), lr = ii - di * (WH * WW), hi = lr / WW, wi = lr - hi * WW;
+        lin_s[ct] = static_cast<short>(di * ((2 * WH - 1) * (2 * WW - 1)) + hi * (2 * WW - 1) + wi);
+      }
+      tc::named_bar_sync(2, 512);
+      const int lin_j = lin_s[jb];
+      const int slice = (g * 2 + half) * 64;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         uint32_t acc[32];      // the TMEM load is warp-collective: never under a divergent branch
-        tc::tmem_ld_32x32b_x32(tmem_base + lane_addr + (g * 2 + half) * 64 + c * 32, acc);
+        tc::tmem_ld_32x32b_x32(tmem_base + lane_addr + slice + c * 32, acc);
         tc::tmem_ld_wait();
         if (j < N) {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) atomicAdd(dst + c * 32 + k, __uint_as_float(acc[k]));
+          for (int k = 0; k < 32; ++k) {
+            const int i = slice + c * 32 + k;
+            if (i < N) atomicAdd(&tab_s[lin_s[i] - lin_j + OFF], __uint_as_float(acc[k]));
+          }
         }
       }
+      tc::named_bar_sync(2, 512);
+      for (int e = ct; e < TL; e += 512) atomicAdd(p.dtable + static_cast<long long>(e) * p.heads + head, tab_s[e]);
     }
   }
   tc::fence_before_sync();
@@ -837,14 +950,16 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
   }
 }
 
-// delta[s, head, i] = sum_e O[row(i), head*32+e] * dO[row(i), head*32+e]  (rowsum(dO * O) of the softmax backward)
+// delta[s, head, i] = sum_e O[row(i), head*32+e] * dO[row(i), head*32+e]  (rowsum(dO * O) of the softmax backward);
+// also zeroes the Q block of dqkv
 template <int WD, int WH, int WW>
 __global__ void __launch_bounds__(256) wattn_delta_kernel(const WinAttnArgs p, float* __restrict__ delta) {
   constexpr int N = WD * WH * WW;
   const int s = blockIdx.x;
+  const WinCoord wc = win_coord(p, s, WD, WH, WW);
   for (int item = threadIdx.x; item < N * p.heads; item += blockDim.x) {
     const int head = item % p.heads, i = item / p.heads;
-    const TokenGeom g = token_geom_t<WD, WH, WW>(p, s, i);
+    const TokenGeom g = token_geom_w<WD, WH, WW>(p, wc, i);
     const uint4* o = reinterpret_cast<const uint4*>(p.out + static_cast<long long>(g.row) * p.C + head * HD);
     const uint4* d = reinterpret_cast<const uint4*>(p.dout + static_cast<long long>(g.row) * p.C + head * HD);
     float acc = 0.f;
@@ -859,6 +974,11 @@ __global__ void __launch_bounds__(256) wattn_delta_kernel(const WinAttnArgs p, f
       }
     }
     delta[(static_cast<long long>(s) * p.heads + head) * NP + i] = acc;
+    // the Q block of dqkv is accumulated with red.add by the two key-half CTAs of the backward kernel: zero it here
+    // (every (token, head) is visited exactly once), which replaces a strided 2-D memset
+    uint4* zq = reinterpret_cast<uint4*>(p.dqkv + static_cast<long long>(g.row) * (3LL * p.C) + head * HD);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) zq[c] = make_uint4(0, 0, 0, 0);
   }
 }
 
@@ -871,15 +991,34 @@ int wattn_tc_bwd(const WinAttnArgs& a, float* delta, cudaStream_t stream) {
   }
   wattn_delta_kernel<6, 7, 6><<<a.S, 256, 0, stream>>>(a, delta);
   VSN_LAUNCH_CHECK();
-  // dQ is accumulated by the two key-half CTAs with bf16x2 red.add: zero the Q block of dqkv first
-  VSN_CUDA(cudaMemset2DAsync(a.dqkv, 3LL * a.C * 2, 0, static_cast<size_t>(a.C) * 2,
-                             static_cast<size_t>(a.B) * a.Dp * a.Hp * a.Wp, stream));
   int groups = vsn_num_sms() / (2 * a.heads);
   if (groups < 1) groups = 1;
   if (groups > a.S) groups = a.S;
   groups = ceil_div(a.S, ceil_div(a.S, groups));
   dim3 grid(groups, a.heads, 2);
+  static int timing = -1;
+  static unsigned long long* tbuf = nullptr;
+  if (timing < 0) {
+    const char* e = getenv("VSN_WATTN_TIMING");
+    timing = (e != nullptr && e[0] == '1') ? 1 : 0;
+    if (timing) {
+      VSN_CUDA(cudaMalloc(&tbuf, 1024 * 16 * 8));
+      VSN_CUDA(cudaMemcpyToSymbol(g_bwd_timing, &tbuf, sizeof(tbuf)));
+    }
+  }
   wattn_bwd_kernel<6, 7, 6><<<grid, BWD_THREADS, SM::TOTAL, stream>>>(a, delta);
   VSN_LAUNCH_CHECK();
+  if (timing) {
+    const int n = grid.x * grid.y * grid.z;
+    static unsigned long long host[1024 * 16];
+    VSN_CUDA(cudaStreamSynchronize(stream));
+    VSN_CUDA(cudaMemcpy(host, tbuf, n * 16 * 8, cudaMemcpyDeviceToHost));
+    double acc[16] = {0};
+    for (int i = 0; i < n; ++i) for (int k = 0; k < 16; ++k) acc[k] += static_cast<double>(host[i * 16 + k]) / n;
+    fprintf(stderr, "wattn_bwd timing (mean cycles per CTA over %d CTAs, %.0f sub-tiles): MMA warp total %.0f | wait ld_full %.0f "
+            "| wait p_ready %.0f | wait acc_read %.0f || group0: wait s_full %.0f ldtm %.0f math %.0f store+arrive %.0f || "
+            "group1: wait s_full %.0f ldtm %.0f math %.0f store+arrive %.0f readout %.0f\n", n, acc[4], acc[0], acc[1], acc[2], acc[3],
+            acc[5], acc[6], acc[7], acc[8], acc[10], acc[11], acc[12], acc[13], acc[14]);
+  }
   return 0;
 }

@@ -12,7 +12,8 @@ struct WinAttnArgs {
   // backward only
   const bf16* dout;     // [T, C]
   bf16* dqkv;           // [T, 3C]
-  float* dbias_dense;   // [heads, 256, 256] fp32, zeroed by the caller; element (a, key j, query i)
+  float* dbias_dense;   // unused by the tcgen05 path (scratch of the mma.sync path)
+  float* dtable;        // [table_len, heads] fp32 gradient of the bias table, accumulated (+=); may be null
   int S, N, heads, C;
   float scale;
   int B, Dp, Hp, Wp, wd, wh, ww, sd, sh, sw, nWd, nWh, nWw, use_mask;
@@ -21,6 +22,6 @@ struct WinAttnArgs {
 // true when the tcgen05 kernels cover this problem (head_dim 32, window (6,7,6))
 bool wattn_tc_supported(int wd, int wh, int ww, int hd);
 int wattn_tc_fwd(const WinAttnArgs& a, cudaStream_t stream);
-// delta [S, heads, 256] = rowsum(dO * O); lse is the log2-domain logsumexp written by wattn_tc_fwd;
-// dbias_dense is [heads][key][query] (transposed with respect to the mma.sync path).
+// delta [S, heads, 256] (scratch) = rowsum(dO * O); lse is the log2-domain logsumexp written by wattn_tc_fwd;
+// the bias-table gradient is folded inside the kernel (no dense [heads,N,N] buffer).
 int wattn_tc_bwd(const WinAttnArgs& a, float* delta, cudaStream_t stream);

@@ -187,7 +187,8 @@ def attn_bwd(qkv, out, dout, lse, heads: int, hd: int, *, S: int, N: int, scale:
     npad = (N + 63) // 64 * 64
     assert dout.dtype == BF16 and dout.is_contiguous()
     delta = torch.empty((S, heads, npad), device=qkv.device, dtype=F32)
-    dense = torch.zeros((heads, npad, npad), device=qkv.device, dtype=F32) if table is not None else None
+    tc_path = geom is not None and hd == 32 and tuple(geom.window) == (6, 7, 6)   # folds the table gradient in-kernel
+    dense = torch.zeros((heads, npad, npad), device=qkv.device, dtype=F32) if (table is not None and not tc_path) else None
     # real tokens are all written by the kernels; padded-grid tokens always belong to a window too
     dqkv = torch.empty_like(qkv)
     if _lib.PROFILE is not None:
