@@ -37,13 +37,16 @@ long long vsn_launch_count(void);
  *   2 multiply by GELU'(aux); resid fp32 [M, ldr] (nullable): out = resid + rowscale * (acc + bias);
  *   row_scale fp32 [M / rows_per_group] (nullable): per-sample DropPath factor; out_kind: 0 bf16 store,
  *   1 fp32 store, 2 fp32 atomic accumulate (required when split_k > 1).
+ *   rowsum_out fp32 [M] (nullable): += sum_k A(m,k), computed on the tensor cores against an all-ones tile --
+ *   in a wgrad GEMM (A = dY read transposed) this is the bias gradient of the Linear, so no separate column
+ *   reduction of dY is needed.
  * Replaces F.linear / nn.Linear forward, dgrad and wgrad on the path:
  *   models/swin_transformer_3d.py:52-69 (MLP), :154-156,166-171,197 (qkv, proj), :550,571 (reduction),
  *   :527-529,539 (Conv3d k=s=patch as a GEMM); models/vit_3d.py:59-75,102-105,113,125,372. */
 int vsn_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, int M, int N, int K,
                   void* out, long long ldo, int out_kind, const float* bias, int act, void* aux, long long ldaux,
                   const float* resid, long long ldr, const float* row_scale, int rows_per_group, float alpha,
-                  int split_k, void* stream);
+                  int split_k, float* rowsum_out, void* stream);
 
 /* ---- LayerNorm --------------------------------------------------------------------------------
  * nn.LayerNorm(C), eps 1e-5: models/swin_transformer_3d.py:236,255,330,373,541,570,693;

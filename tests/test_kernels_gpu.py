@@ -78,6 +78,12 @@ def test_gemm_dgrad_wgrad(M, N, K):
     assert rel_err(dw, ref) < 1e-4
     ops.linear_wgrad(dy, x, dw)           # accumulates
     assert rel_err(dw, 2 * ref) < 1e-4
+    # bias gradient from the same GEMM (row sums of dy^T against an all-ones tile), accumulating
+    db = torch.ones(N, device="cuda")
+    dw2 = torch.zeros_like(dw)
+    ops.linear_wgrad(dy, x, dw2, dbias=db)
+    assert rel_err(dw2, ref) < 1e-4
+    assert rel_err(db - 1, dy.float().sum(0)) < 1e-4
 
 
 # ----------------------------------------------------------------------------- LayerNorm

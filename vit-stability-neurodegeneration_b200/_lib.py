@@ -16,7 +16,7 @@ _p, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 SIGNATURES = {
     "vsn_version": [],
     "vsn_check_device": [],
-    "vsn_gemm_bf16": [_p, _ll, _i, _p, _ll, _i, _i, _i, _i, _p, _ll, _i, _p, _i, _p, _ll, _p, _ll, _p, _i, _f, _i, _p],
+    "vsn_gemm_bf16": [_p, _ll, _i, _p, _ll, _i, _i, _i, _i, _p, _ll, _i, _p, _i, _p, _ll, _p, _ll, _p, _i, _f, _i, _p, _p],
     "vsn_layernorm_fwd": [_p, _ll, _p, _p, _p, _ll, _i, _p, _p, _ll, _i, _f, _p],
     "vsn_layernorm_bwd": [_p, _ll, _i, _p, _ll, _p, _p, _p, _p, _ll, _p, _ll, _p, _ll, _p, _i, _p, _p, _ll, _i, _p],
     "vsn_colreduce": [_p, _ll, _i, _p, _ll, _p, _p, _p, _p, _ll, _i, _p],

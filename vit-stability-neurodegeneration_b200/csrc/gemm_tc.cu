@@ -39,6 +39,7 @@ struct GemmArgs {
   int rows_per_group;
   float alpha;
   int wide;             // 1: out / aux / resid rows are 32-byte aligned -> 256-bit accesses
+  float* rowsum;        // [M] fp32 or null: rowsum[m] += sum_k A(m,k) (bias gradient of a Linear in its wgrad GEMM)
 };
 
 template <int BN>
@@ -46,8 +47,10 @@ struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
-  static constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;   // two accumulator buffers
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias*/;
+  static constexpr int RS_COL = 2 * BN;              // two 16-column row-sum accumulators after the two tiles
+  static constexpr int TMEM_COLS = 2 * BN + 32 <= 128 ? 128 : 2 * BN + 32 <= 256 ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias*/ +
+                                    2048 /*ones tile*/;
 };
 
 
@@ -216,6 +219,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
   uint64_t* acc_empty = acc_full + 2;             // [2] epilogue threads -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* bias_s = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);   // [2][256]
+  uint8_t* ones_s = smem + C::STAGES * C::STAGE_BYTES + 256 + 2048;                     // [16][64] bf16, all 1.0
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -235,6 +239,10 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
     tc::prefetch_tmap(&tmB);
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, C::TMEM_COLS);
+  if (p.rowsum != nullptr) {
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) reinterpret_cast<uint32_t*>(ones_s)[i] = 0x3F803F80u;   // bf16 1.0 pairs
+    tc::fence_proxy_async();
+  }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -271,6 +279,8 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = tc::make_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+      const uint32_t idesc_rs = tc::make_idesc_bf16(BM, 16, p.a_mn, 0);
+      const uint64_t ones_desc = tc::make_smem_desc_sw128(tc::smem_u32(ones_s), 16, 1024);
       const uint32_t a_step = p.a_mn ? 2048u : 32u;   // bytes per K=16 step
       const uint32_t b_step = p.b_mn ? 2048u : 32u;
       const uint32_t a_lbo = p.a_mn ? 8192u : 16u;
@@ -282,6 +292,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
         tc::mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);
         tc::fence_after_sync();
         const uint32_t d = tmem_base + buf * BN;
+        const bool do_rs = p.rowsum != nullptr && t.n0 == 0 && C::RS_COL + 32 <= C::TMEM_COLS;
         for (int i = 0; i < t.nkb; ++i, ++it) {
           const int s = it % C::STAGES;
           const uint32_t ph = (it / C::STAGES) & 1;
@@ -295,6 +306,8 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
             const uint64_t ad = tc::make_smem_desc_sw128(sa + k * a_step, a_lbo, 1024);
             const uint64_t bd = tc::make_smem_desc_sw128(sb + k * b_step, b_lbo, 1024);
             tc::mma_bf16_ss(d, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            // row sums of A on the tensor cores: one N=16 MMA against the all-ones tile (first n-tile only)
+            if (do_rs) tc::mma_bf16_ss(tmem_base + C::RS_COL + buf * 16, ad, ones_desc, idesc_rs, (i > 0 || k > 0) ? 1u : 0u);
           }
           tc::mma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs retire
         }
@@ -350,6 +363,11 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
           const int n = t.n0 + c0;
           if (row_ok && n < p.N) epilogue_chunk(p, row, n, rs, v, bs + c0);
         }
+      }
+      if (p.rowsum != nullptr && t.n0 == 0 && par == 0 && C::RS_COL + 32 <= C::TMEM_COLS) {
+        const uint32_t rsv = tc::tmem_ld_32x32b_x1(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + C::RS_COL + buf * 16);
+        tc::tmem_ld_wait();
+        if (row_ok) atomicAdd(p.rowsum + row, __uint_as_float(rsv));
       }
       tc::fence_before_sync();
       tc::mbar_arrive(&acc_empty[buf]);
@@ -425,7 +443,7 @@ int forced_ew() {
 extern "C" int vsn_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, int M,
                              int N, int K, void* out, long long ldo, int out_kind, const float* bias, int act,
                              void* aux, long long ldaux, const float* resid, long long ldr, const float* row_scale,
-                             int rows_per_group, float alpha, int split_k, void* stream) {
+                             int rows_per_group, float alpha, int split_k, float* rowsum_out, void* stream) {
   VSN_CHECK(M > 0 && N > 0 && K > 0, "vsn_gemm_bf16: empty problem %d x %d x %d", M, N, K);
   VSN_CHECK(out_kind >= 0 && out_kind <= 2, "vsn_gemm_bf16: bad out_kind %d", out_kind);
   VSN_CHECK(act == 0 || aux != nullptr, "vsn_gemm_bf16: activation modes need the aux buffer");
@@ -443,6 +461,7 @@ extern "C" int vsn_gemm_bf16(const void* A, long long lda, int a_mn, const void*
   else if (N <= 64) BN = 64;
   else if (N <= 96) BN = 96;
   else BN = 128;
+  if (rowsum_out != nullptr && BN == 256) BN = 128;   // the row-sum accumulators need 32 spare TMEM columns
   {
     const int want = vsn_num_sms();
     const int sk = split_k < 1 ? 1 : split_k;
@@ -480,6 +499,7 @@ extern "C" int vsn_gemm_bf16(const void* A, long long lda, int a_mn, const void*
     if (resid != nullptr) wide = wide && (reinterpret_cast<uintptr_t>(resid) % 32 == 0) && ((ldr * 4) % 32 == 0);
     a.wide = wide ? 1 : 0;
   }
+  a.rowsum = rowsum_out;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   int ew = (K <= 256 && out_kind != 2) ? 16 : 8;
   if (forced_ew() == 8 || forced_ew() == 16) ew = forced_ew();

@@ -34,7 +34,7 @@ def _require_cuda(*ts):
 
 # ------------------------------------------------------------------ GEMM family
 def gemm(a, lda, a_mn, b, ldb, b_mn, M, N, K, out, ldo, out_kind, *, bias=None, act=0, aux=None, ldaux=0,
-         resid=None, ldr=0, row_scale=None, rows_per_group=1, alpha=1.0, split_k=1):
+         resid=None, ldr=0, row_scale=None, rows_per_group=1, alpha=1.0, split_k=1, rowsum=None):
     _require_cuda(a, b, out)
     if _lib.PROFILE is not None:
         _lib.TAG = f"M{M} N{N} K{K} majors={int(a_mn)}{int(b_mn)} out={out_kind} act={act}"
@@ -42,7 +42,7 @@ def gemm(a, lda, a_mn, b, ldb, b_mn, M, N, K, out, ldo, out_kind, *, bias=None, 
                      + (M * N * 4 if resid is not None else 0) + (M * N * 2 if act else 0))
     _lib.call("vsn_gemm_bf16", _p(a), lda, int(a_mn), _p(b), ldb, int(b_mn), M, N, K, _p(out), ldo, out_kind,
               _p(bias), act, _p(aux), ldaux, _p(resid), ldr, _p(row_scale), rows_per_group, float(alpha), split_k,
-              _stream())
+              _p(rowsum), _stream())
 
 
 def linear_fwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, out_dtype=BF16,
@@ -76,15 +76,16 @@ def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, *, gelu_aux: Optional[torch.
     return out
 
 
-def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor) -> None:
-    """dw[N,K] += dy[M,N].T @ x[M,K]  (both operands MN-major, tokens split over CTAs, fp32 atomics)."""
+def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, dbias: Optional[torch.Tensor] = None) -> None:
+    """dw[N,K] += dy[M,N].T @ x[M,K]  (both operands MN-major, tokens split over CTAs, fp32 atomics).
+    With dbias (fp32 [N]) the bias gradient dbias[n] += sum_m dy[m,n] is produced by the same GEMM."""
     M, N = dy.shape
     K = x.shape[1]
     assert dy.dtype == BF16 and x.dtype == BF16 and dw.dtype == F32 and dw.is_contiguous()
     tiles = math.ceil(N / 128) * math.ceil(K / (64 if K <= 64 else 128))
     nkb = math.ceil(M / 64)
     split = max(1, min(nkb, (2 * _N_SMS) // max(tiles, 1)))
-    gemm(dy, dy.stride(0), 1, x, x.stride(0), 1, N, K, M, dw, K, 2, split_k=split)
+    gemm(dy, dy.stride(0), 1, x, x.stride(0), 1, N, K, M, dw, K, 2, split_k=split, rowsum=dbias)
 
 
 # ------------------------------------------------------------------ LayerNorm

@@ -118,30 +118,28 @@ class SwinBlockFn(torch.autograd.Function):
         dev = x.device
         C = x.shape[1]
         g = _contig_f32(g)
-        z = lambda *s: torch.zeros(s, device=dev, dtype=F32)  # noqa: E731
-        d_qkv_w, d_proj_w, d_fc1_w, d_fc2_w = (z(*s) for s in ctx.shapes)
-        d_qkv_b, d_proj_b, d_fc1_b, d_fc2_b = z(ctx.shapes[0][0]), z(C), z(w1.shape[0]), z(C)
-        d_n1w, d_n1b, d_n2w, d_n2b = z(C), z(C), z(C), z(C)
-        d_table = torch.zeros_like(table) if table is not None else None
+        # all parameter-gradient accumulators of the block come from ONE zero-filled buffer (one fill kernel
+        # instead of 13); every kernel below accumulates (+=) into its slice
+        shapes = [*ctx.shapes, (ctx.shapes[0][0],), (C,), (w1.shape[0],), (C,), (C,), (C,), (C,), (C,)]
+        if table is not None:
+            shapes.append(tuple(table.shape))
+        (d_qkv_w, d_proj_w, d_fc1_w, d_fc2_w, d_qkv_b, d_proj_b, d_fc1_b, d_fc2_b, d_n1w, d_n1b, d_n2w, d_n2b,
+         *rest) = zeros_like_shapes(shapes, dev)
+        d_table = rest[0] if table is not None else None
         # ---- MLP branch: x2 = x1 + s2 * (W2 gelu(W1 LN2(x1) + b1) + b2)
         gs = ops.cast_rows_bf16(g, cfg.scale2, tps)
-        ops.colsum(gs, d_fc2_b)
-        ops.linear_wgrad(gs, a, d_fc2_w)
+        ops.linear_wgrad(gs, a, d_fc2_w, dbias=d_fc2_b)
         dh = ops.linear_dgrad(gs, w2, gelu_aux=h)
-        ops.colsum(dh, d_fc1_b)
-        ops.linear_wgrad(dh, y2, d_fc1_w)
+        ops.linear_wgrad(dh, y2, d_fc1_w, dbias=d_fc1_b)
         dy2 = ops.linear_dgrad(dh, w1)
         g1, g1s = ops.layernorm_bwd(dy2, x1, mean2, rstd2, n2w, resid_grad=g, want_bf16=True, row_scale=cfg.scale1,
                                     rows_per_group=tps, dgamma=d_n2w, dbeta=d_n2b)
         # ---- attention branch: x1 = x + s1 * (Wp attn(Wq LN1(x) + bq) + bp)
-        ops.colsum(g1s, d_proj_b)
-        ops.linear_wgrad(g1s, o, d_proj_w)
+        ops.linear_wgrad(g1s, o, d_proj_w, dbias=d_proj_b)
         do = ops.linear_dgrad(g1s, wp)
         dqkv = ops.attn_bwd(qkv, o, do, lse, cfg.heads, cfg.hd, S=S, N=N, scale=cfg.hd ** -0.5, geom=geom,
                             table=table, dtable=d_table)
-        if ctx.has_qkv_bias:
-            ops.colsum(dqkv, d_qkv_b)
-        ops.linear_wgrad(dqkv, y1, d_qkv_w)
+        ops.linear_wgrad(dqkv, y1, d_qkv_w, dbias=d_qkv_b if ctx.has_qkv_bias else None)
         dy1 = ops.linear_dgrad(dqkv, wq)
         g0, _ = ops.layernorm_bwd(dy1, x, mean1, rstd1, n1w, resid_grad=g1, dx_out=g1, dgamma=d_n1w, dbeta=d_n1b)
         return (g0, d_n1w, d_n1b, d_qkv_w, d_qkv_b if ctx.has_qkv_bias else None, d_table, d_proj_w, d_proj_b,
@@ -181,8 +179,7 @@ class PatchEmbedFn(torch.autograd.Function):
             (rows,) = ctx.saved_tensors
             d_nw = d_nb = None
             dyb = ops.cast_rows_bf16(g)
-        ops.colsum(dyb, d_b)
-        ops.linear_wgrad(dyb, rows, d_w)
+        ops.linear_wgrad(dyb, rows, d_w, dbias=d_b)
         return None, d_w.view(ctx.wshape), d_b, d_nw, d_nb, None, None
 
 
@@ -271,6 +268,17 @@ class NormPoolHeadFn(torch.autograd.Function):
 # --------------------------------------------------------------------------------------
 # helpers shared by the drop-in modules
 # --------------------------------------------------------------------------------------
+def zeros_like_shapes(shapes, device) -> List[torch.Tensor]:
+    """fp32 zero tensors of the given shapes carved out of a single zero-filled allocation (16-byte aligned slices)."""
+    sizes = [1 if len(s) == 0 else int(torch.Size(s).numel()) for s in shapes]
+    offs, tot = [], 0
+    for n in sizes:
+        offs.append(tot)
+        tot += (n + 3) // 4 * 4
+    flat = torch.zeros(tot, device=device, dtype=F32)
+    return [flat[o: o + n].view(tuple(s)) for o, n, s in zip(offs, sizes, shapes)]
+
+
 def padded_dims(real: Sequence[int], window: Sequence[int]) -> Tuple[int, int, int]:
     return tuple((r + w - 1) // w * w for r, w in zip(real, window))
 

@@ -46,8 +46,7 @@ class ViTEmbedFn(torch.autograd.Function):
         ops.ln_param_grad(demb, z, m2, r2, d_ln2w, d_ln2b)
         _, dzb = ops.layernorm_bwd(demb, z, m2, r2, ln2w, want_dx=False, want_bf16=True)
         d_lin_b, d_lin_w = zeros(C), zeros(*wshape)
-        ops.colsum(dzb, d_lin_b)
-        ops.linear_wgrad(dzb, y1, d_lin_w)
+        ops.linear_wgrad(dzb, y1, d_lin_w, dbias=d_lin_b)
         dy1 = ops.linear_dgrad(dzb, w16)
         d_ln1w, d_ln1b = zeros(P), zeros(P)
         ops.ln_param_grad(dy1, rows, m1, r1, d_ln1w, d_ln1b)
