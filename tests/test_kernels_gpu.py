@@ -197,6 +197,20 @@ def test_patch_gather_bit_exact(dtype):
     assert torch.equal(rows, ref)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 12, 20, 16), (1, 10, 13, 8), (3, 144, 168, 144)])
+def test_patch_gather_444_fast_path_bit_exact(dtype, shape):
+    """bf16 rows of 4x4x4 patches with W % 4 == 0 take the vectorised kernel (one 32-byte store per (token, i))."""
+    ops = _ops()
+    B, D, H, W = shape
+    vol = _rand(B, 1, D, H, W, seed=1).to(dtype)
+    rows = ops.patch_gather(vol, (4, 4, 4))
+    v = torch.nn.functional.pad(vol.float(), (0, 0, 0, (-H) % 4, 0, (-D) % 4))
+    gd, gh, gw = v.shape[2] // 4, v.shape[3] // 4, v.shape[4] // 4
+    ref = v.reshape(B, gd, 4, gh, 4, gw, 4).permute(0, 1, 3, 5, 2, 4, 6).reshape(B * gd * gh * gw, 64)
+    assert rows.dtype == torch.bfloat16 and torch.equal(rows, ref.to(torch.bfloat16))
+
+
 def test_grid_copy_and_merge_gather_bit_exact():
     ops = _ops()
     B, C = 2, 32

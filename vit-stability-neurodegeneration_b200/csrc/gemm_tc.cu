@@ -501,7 +501,7 @@ extern "C" int vsn_gemm_bf16(const void* A, long long lda, int a_mn, const void*
   }
   a.rowsum = rowsum_out;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  int ew = (K <= 256 && out_kind != 2) ? 16 : 8;
+  int ew = ((K <= 256 || act == 2) && out_kind != 2) ? 16 : 8;
   if (forced_ew() == 8 || forced_ew() == 16) ew = forced_ew();
   if (ew == 16) {
     switch (BN) {

@@ -47,6 +47,57 @@ __global__ void patch_gather_kernel(const InT* __restrict__ vol, OutT* __restric
   }
 }
 
+
+// Fast path for 4x4x4 patches (the Swin patch embedding): one thread per (token, i) reads the four 4-voxel rows
+// j = 0..3 (consecutive threads walk w, so each row load of a warp is contiguous) and writes the 16 outputs
+// as one full 32-byte sector.  W % 4 == 0 and a 4-voxel aligned volume row are required.
+template <typename InT>
+__device__ __forceinline__ void load4(const InT* p, float* v);
+template <>
+__device__ __forceinline__ void load4<float>(const float* p, float* v) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <>
+__device__ __forceinline__ void load4<__half>(const __half* p, float* v) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+template <>
+__device__ __forceinline__ void load4<bf16>(const bf16* p, float* v) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
+template <typename InT>
+__global__ void __launch_bounds__(256) patch_gather444_kernel(const InT* __restrict__ vol, bf16* __restrict__ out, int B,
+                                                              int D, int H, int W, int gd, int gh, int gw) {
+  const long long total = static_cast<long long>(B) * gd * gh * 4 * gw;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    long long t = idx;
+    const int w = static_cast<int>(t % gw); t /= gw;
+    const int i = static_cast<int>(t & 3); t >>= 2;
+    const int h = static_cast<int>(t % gh); t /= gh;
+    const int d = static_cast<int>(t % gd); t /= gd;
+    const int b = static_cast<int>(t);
+    const int zd = d * 4 + i;
+    uint32_t o[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int zh = h * 4 + j;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (zd < D && zh < H) load4<InT>(vol + ((static_cast<long long>(b) * D + zd) * H + zh) * W + w * 4, v);
+      o[2 * j] = pack_bf16(v[0], v[1]);
+      o[2 * j + 1] = pack_bf16(v[2], v[3]);
+    }
+    const long long token = ((static_cast<long long>(b) * gd + d) * gh + h) * gw + w;
+    st_global_v8(out + token * 64 + i * 16, o);
+  }
+}
+
 // Copy the overlapping box of two channels-last grids and zero-fill the rest of dst.
 // pad (models/swin_transformer_3d.py:457-461) when dst is larger, crop (:508) when smaller.
 __global__ void grid_copy_kernel(const float* __restrict__ src, int sD, int sH, int sW, float* __restrict__ dst,
@@ -223,6 +274,17 @@ extern "C" int vsn_patch_gather(const void* vol, int in_dtype, void* out, int ou
   const long long total = static_cast<long long>(B) * gd * gh * gw * pd * ph;
   if (total == 0) return 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (pd == 4 && ph == 4 && pw == 4 && out_bf16 && W % 4 == 0 && in_dtype >= 0 && in_dtype <= 2 &&
+      (reinterpret_cast<uintptr_t>(vol) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 32 == 0)) {
+    const long long items = static_cast<long long>(B) * gd * gh * 4 * gw;
+    const unsigned g4 = grid_for(items, 256);
+    bf16* o = reinterpret_cast<bf16*>(out);
+    if (in_dtype == 0) patch_gather444_kernel<float><<<g4, 256, 0, s>>>(reinterpret_cast<const float*>(vol), o, B, D, H, W, gd, gh, gw);
+    else if (in_dtype == 1) patch_gather444_kernel<__half><<<g4, 256, 0, s>>>(reinterpret_cast<const __half*>(vol), o, B, D, H, W, gd, gh, gw);
+    else patch_gather444_kernel<bf16><<<g4, 256, 0, s>>>(reinterpret_cast<const bf16*>(vol), o, B, D, H, W, gd, gh, gw);
+    VSN_LAUNCH_CHECK();
+    return 0;
+  }
   const unsigned grid = grid_for(total, 256);
 #define VSN_PG(InT, OutT)                                                                                          \
   patch_gather_kernel<InT, OutT><<<grid, 256, 0, s>>>(reinterpret_cast<const InT*>(vol), reinterpret_cast<OutT*>(out), \
