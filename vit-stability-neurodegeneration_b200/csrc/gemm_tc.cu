@@ -26,6 +26,7 @@ struct GemmArgs {
   int kb_per_split;     // k-blocks handled by one split
   int splits;           // K splits per output tile (fp32 atomic accumulation when > 1)
   int total_tiles;      // tiles_m * tiles_n * splits
+  int stationary;       // 1: CTA b keeps column (n-tile, split) = b % cols for all its m-tiles (cols divides the grid)
   void* out;
   long long ldo;
   int out_kind;         // 0 bf16 store, 1 fp32 store, 2 fp32 atomic add
@@ -65,6 +66,22 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmArgs& p, int tile, in
   t.kb0 = split * p.kb_per_split;
   t.nkb = min(nkb_total, t.kb0 + p.kb_per_split) - t.kb0;
   return t;
+}
+// k-th tile of this CTA, or false when it has none left.  Stationary schedule: the CTA keeps its
+// (n-tile, split) column and walks the m-tiles with stride gridDim.x / columns, so the weight tile and the
+// bias slice stay the same for the whole kernel; otherwise tiles are dealt round-robin.
+__device__ __forceinline__ bool cta_tile(const GemmArgs& p, int k, int tiles_n, int bn, TileCoord& t) {
+  if (p.stationary) {
+    const int cols = tiles_n * p.splits;
+    const int col = blockIdx.x % cols, m_tile = blockIdx.x / cols + k * (gridDim.x / cols);
+    if (m_tile * BM >= p.M) return false;
+    t = decode_tile(p, m_tile * cols + col, tiles_n, bn);
+    return true;
+  }
+  const int tile = blockIdx.x + k * gridDim.x;
+  if (tile >= p.total_tiles) return false;
+  t = decode_tile(p, tile, tiles_n, bn);
+  return true;
 }
 
 // One 32-column chunk of an output row: v = fp32 accumulators from TMEM, bias_s = the chunk's bias in smem.
@@ -251,8 +268,8 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;   // k-blocks issued so far (ring position)
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile, tiles_n, BN);
+      TileCoord t;
+      for (int lt = 0; cta_tile(p, lt, tiles_n, BN, t); ++lt) {
         for (int i = 0; i < t.nkb; ++i, ++it) {
           const int s = it % C::STAGES;
           const uint32_t ph = (it / C::STAGES) & 1;
@@ -285,9 +302,9 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
       const uint32_t b_step = p.b_mn ? 2048u : 32u;
       const uint32_t a_lbo = p.a_mn ? 8192u : 16u;
       const uint32_t b_lbo = p.b_mn ? 8192u : 16u;
-      int it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
-        const TileCoord t = decode_tile(p, tile, tiles_n, BN);
+      int it = 0;
+      TileCoord t;
+      for (int lt = 0; cta_tile(p, lt, tiles_n, BN, t); ++lt) {
         const int buf = lt & 1;
         tc::mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);
         tc::fence_after_sync();
@@ -321,15 +338,15 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
     const int par = (warp - 2) >> 2;             // which chunks of the tile
     const int et = threadIdx.x - 64;
     constexpr int NCH = (BN / 32 + NPAR - 1) / NPAR;   // chunks per warp (upper bound)
-    int lt = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
-      const TileCoord t = decode_tile(p, tile, tiles_n, BN);
+    TileCoord t;
+    for (int lt = 0; cta_tile(p, lt, tiles_n, BN, t); ++lt) {
       const int buf = lt & 1;
       const int row = t.m0 + lg * 32 + lane;
-      float* bs = bias_s + buf * 256;
-      if (p.bias != nullptr) {
-        // the tile's bias slice goes through smem: one coalesced load per tile instead of 8 dependent
-        // global loads per chunk and thread (the buffer's previous readers finished two tiles ago)
+      // The tile's bias slice goes through smem (broadcast reads instead of dependent global loads per chunk).
+      // Stationary schedule: staged once, the column never changes; otherwise once per tile into the buffer
+      // whose previous readers finished two tiles ago.
+      float* bs = bias_s + (p.stationary ? 0 : buf * 256);
+      if (p.bias != nullptr && (lt == 0 || !p.stationary)) {
         if (et < BN) bs[et] = (t.n0 + et < p.N) ? p.bias[t.n0 + et] : 0.f;
         tc::named_bar_sync(1, EPI_THREADS);
       }
@@ -424,8 +441,17 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs a, int split
     attr_set = true;
   }
   a.splits = splits;
-  a.total_tiles = ceil_div(a.M, BM) * ceil_div(a.N, BN) * splits;
-  const int grid = a.total_tiles < vsn_num_sms() ? a.total_tiles : vsn_num_sms();
+  const int tiles_m = ceil_div(a.M, BM), cols = ceil_div(a.N, BN) * splits;
+  a.total_tiles = tiles_m * cols;
+  int grid = a.total_tiles < vsn_num_sms() ? a.total_tiles : vsn_num_sms();
+  a.stationary = 0;
+  // (measured: pays for few wide column tiles; round-robin is better for split-K and for many / narrow columns)
+  if (splits == 1 && (cols == 1 || (BN >= 128 && cols <= 4)) && tiles_m >= 2 * (vsn_num_sms() / cols)) {
+    // n-stationary persistent schedule: as many rows of `cols` CTAs as fit on the chip
+    const int rows = vsn_num_sms() / cols < tiles_m ? vsn_num_sms() / cols : tiles_m;
+    grid = rows * cols;
+    a.stationary = 1;
+  }
   gemm_tc_kernel<BN, EW><<<grid, 64 + EW * 32, Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, a);
   VSN_LAUNCH_CHECK();
   return 0;
