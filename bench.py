@@ -397,6 +397,25 @@ def main():
                     wa[key] = {"shape": r["shape"], "tflops": r["tflops"], "frac_of_peak": round(r["tflops"] / tc_peak, 4),
                                "ms_total": r["ms_total"]}
         roofline["window_attention"] = wa
+        # HBM-bound kernel families of the path (LayerNorm, casts, SAM/EMA): achieved GB/s of the heaviest shape
+        hb = {}
+        for r in table:
+            if r["call"] in ("vsn_layernorm_fwd", "vsn_layernorm_bwd", "vsn_cast_rows_bf16", "vsn_mt_ema", "vsn_mt_cast_bf16",
+                             "vsn_merge_gather", "vsn_patch_gather") and "gbs" in r:
+                if r["call"] not in hb or r["ms_total"] > hb[r["call"]]["ms_total"]:
+                    hb[r["call"]] = {"shape": r["shape"], "gbs": r["gbs"], "frac_of_hbm_peak": round(r["gbs"] / hbm_peak, 3),
+                                     "ms_total": r["ms_total"]}
+        roofline["hbm_kernels"] = hb
+        # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/ncu_traffic.json)
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                tr = json.load(f)
+            ent = tr.get(f"{name}|{tag}")
+            if ent:
+                roofline["traffic"] = ent["dram_bytes_per_launch"]
+                roofline["traffic_source"] = ent["source"]
+        except OSError:
+            pass
         if args.profile_out:
             os.makedirs(os.path.dirname(os.path.abspath(args.profile_out)), exist_ok=True)
             with open(args.profile_out, "w") as f:
