@@ -65,6 +65,30 @@ def test_gemm_epilogues():
     assert rel_err(dx.float(), a.grad) < BF16_TOL
 
 
+def test_gemm_gelu_epilogue_accuracy_wide_range():
+    """The packed (half2) GELU / GELU' of the epilogue against torch's exact erf GELU on pre-activations that span
+    [-12, 12] (identity weights make the pre-activation equal to the input): element-wise error bounded by the bf16
+    output rounding, not by the fp16 polynomial."""
+    ops = _ops()
+    M, K = 1024, 128
+    x = torch.linspace(-12, 12, M * K, device="cuda").reshape(M, K)
+    x = x[:, torch.randperm(K, device="cuda")].contiguous()
+    xb = _bf(x)
+    eye = _bf(torch.eye(K, device="cuda"))
+    aux = torch.empty(M, K, device="cuda", dtype=torch.bfloat16)
+    y = ops.linear_fwd(xb, eye, None, gelu_aux=aux)
+    assert torch.equal(aux, xb)
+    ref = torch.nn.functional.gelu(xb.float())
+    assert float((y.float() - ref).abs().max()) < 2 ** -7 * 12                     # bf16 half-ulp at |y| <= 12 plus margin
+    assert float(((y.float() - ref).abs() / (ref.abs() + 1e-2)).max()) < 2e-2
+    dy = _bf(torch.ones(M, K, device="cuda"))
+    dx = ops.linear_dgrad(dy, eye, gelu_aux=aux)
+    a = xb.float().requires_grad_(True)
+    torch.nn.functional.gelu(a).sum().backward()
+    assert float((dx.float() - a.grad).abs().max()) < 1.5e-2
+    assert rel_err(dx.float(), a.grad) < 5e-3
+
+
 @pytest.mark.parametrize("M,N,K", [(512, 96, 96), (3000, 288, 96), (1000, 96, 384), (700, 384, 96),
                                    (5000, 192, 768), (64, 96, 64), (100, 1536, 384)])
 def test_gemm_dgrad_wgrad(M, N, K):

@@ -79,6 +79,7 @@ def test_swin_matches_reference(name):
                         masks=iter(torch.from_numpy(mm) for mm in masks))
     O.soft_target_ce(zo, tgt.cpu(), 0.1).backward()
     worst = _grad_report(model, {k: sd[k].grad for k in m["param_order"]}, g)
+    print("WORST_GRAD", name, worst)
     assert worst[1] < TOL, worst
 
 

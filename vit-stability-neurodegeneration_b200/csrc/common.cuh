@@ -111,6 +111,67 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 __device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
+
+// ---- packed (half2) GELU for GEMM epilogues --------------------------------------------------------------------
+// The epilogue of the MLP GEMMs is bound by instruction issue, and its output is rounded to bf16 (2^-9) anyway:
+// the erf polynomial, the exponential (ex2.approx.f16x2: two per MUFU) and the final products run two elements
+// per instruction in fp16 (2^-11).  Inputs are bf16-representable values, exact in fp16 for |x| < 65504.
+__device__ __forceinline__ uint32_t h2_ex2(uint32_t x) {
+  uint32_t y;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+__device__ __forceinline__ __half2 h2_from_u32(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ uint32_t h2_to_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+// 0.5 * erfc(|x| / sqrt(2)) = 1 - Phi(|x|) for two values (no cancellation in the tails)
+__device__ __forceinline__ __half2 h2_half_erfc(__half2 ax) {
+  const __half2 z = __hmin2(__hmul2(ax, __float2half2_rn(0.70710678f)), __float2half2_rn(4.0f));
+  __half2 q = __hfma2(z, __float2half2_rn(0.000233418324f), __float2half2_rn(-0.00402740239f));   // -q(z)
+  q = __hfma2(q, z, __float2half2_rn(0.031229802f));
+  q = __hfma2(q, z, __float2half2_rn(-0.149565667f));
+  q = __hfma2(q, z, __float2half2_rn(-0.918361976f));
+  q = __hfma2(q, z, __float2half2_rn(-1.62790073f));
+  return h2_from_u32(h2_ex2(h2_to_u32(__hfma2(z, q, __float2half2_rn(-1.0f)))));                   // 2^(-z q - 1)
+}
+// exponent argument -(z q(z)) - 1 of 0.5 * erfc(|x| / sqrt(2)) for two values (fp16 polynomial)
+__device__ __forceinline__ __half2 h2_half_erfc_arg(__half2 ax) {
+  const __half2 z = __hmin2(__hmul2(ax, __float2half2_rn(0.70710678f)), __float2half2_rn(4.0f));
+  __half2 q = __hfma2(z, __float2half2_rn(0.000233418324f), __float2half2_rn(-0.00402740239f));   // -q(z)
+  q = __hfma2(q, z, __float2half2_rn(0.031229802f));
+  q = __hfma2(q, z, __float2half2_rn(-0.149565667f));
+  q = __hfma2(q, z, __float2half2_rn(-0.918361976f));
+  q = __hfma2(q, z, __float2half2_rn(-1.62790073f));
+  return __hfma2(z, q, __float2half2_rn(-1.0f));
+}
+// GELU of the two bf16 values packed in `pk` (low = element 0), results as fp32:
+// gelu(x) = max(x, 0) - |x| * (1 - Phi(|x|)).  The polynomial runs packed in fp16; the exponential and the final
+// combination stay in fp32 (ex2.approx.f16x2 is only 2^-9.9 accurate and its error does not average out over the
+// token sums of the weight gradients).
+__device__ __forceinline__ float2 gelu_erf_bf16x2(uint32_t pk) {
+  const float x0 = bf16lo(pk), x1 = bf16hi(pk);
+  const __half2 x = __floats2half2_rn(x0, x1);
+  const float2 arg = __half22float2(h2_half_erfc_arg(h2_from_u32(h2_to_u32(x) & 0x7FFF7FFFu)));
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(arg.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(arg.y));
+  return make_float2(fmaf(-fabsf(x0), e0, fmaxf(x0, 0.f)), fmaf(-fabsf(x1), e1, fmaxf(x1, 0.f)));
+}
+// GELU'(x) = Phi(x) + x * phi(x) of the two bf16 values packed in `pk`, results as fp32.
+// Phi(x) = x < 0 ? (1 - Phi(|x|)) : Phi(|x|), selected per half with a sign mask (no cancellation for x < 0).
+__device__ __forceinline__ float2 gelu_erf_grad_bf16x2(uint32_t pk) {
+  const __half2 x = __floats2half2_rn(bf16lo(pk), bf16hi(pk));
+  const uint32_t xu = h2_to_u32(x);
+  const __half2 ax = h2_from_u32(xu & 0x7FFF7FFFu);
+  const __half2 he = h2_half_erfc(ax);
+  const uint32_t m = ((xu >> 15) & 0x00010001u) * 0xFFFFu;                         // 0xFFFF where x < 0
+  const uint32_t hi = h2_to_u32(__hsub2(__float2half2_rn(1.0f), he));
+  const __half2 cdf = h2_from_u32((h2_to_u32(he) & m) | (hi & ~m));
+  const __half2 axc = __hmin2(ax, __float2half2_rn(8.0f));                          // phi(8) ~ 5e-15
+  const __half2 g = h2_from_u32(h2_ex2(h2_to_u32(__hmul2(__hmul2(axc, axc), __float2half2_rn(-0.72134752f)))));
+  const float2 c = __half22float2(cdf), gg = __half22float2(g), xf = __half22float2(x);
+  return make_float2(fmaf(xf.x * 0.39894228f, gg.x, c.x), fmaf(xf.y * 0.39894228f, gg.y, c.y));
+}
+
 // 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): a thread that owns a contiguous run of a row reads or
 // writes whole 32-byte sectors with one instruction.  The address must be 32-byte aligned.
 __device__ __forceinline__ void st_global_v8(void* p, const uint32_t* v) {

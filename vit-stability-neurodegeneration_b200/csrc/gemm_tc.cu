@@ -40,6 +40,8 @@ struct GemmArgs {
   int rows_per_group;
   float alpha;
   int wide;             // 1: out / aux / resid rows are 32-byte aligned -> 256-bit accesses
+  int gelu_fp32;        // bit 0: GELU in fp32 (default: the forward activation feeds every later layer and the
+                        // model-level gradient parity needs it), bit 1: GELU' in fp32 (default: packed half2)
   float* rowsum;        // [M] fp32 or null: rowsum[m] += sum_k A(m,k) (bias gradient of a Linear in its wgrad GEMM)
 };
 
@@ -115,10 +117,19 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, int row, int n
     } else {
       _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { ap[j] = __float2bfloat16(f[j]); }
     }
+    if (p.gelu_fp32 & 1) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      f[2 * j] = gelu_erf<false>(bf16lo(pk[j]));
-      f[2 * j + 1] = gelu_erf<true>(bf16hi(pk[j]));
+      for (int j = 0; j < 16; ++j) {
+        f[2 * j] = gelu_erf<false>(bf16lo(pk[j]));
+        f[2 * j + 1] = gelu_erf<false>(bf16hi(pk[j]));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float2 y = gelu_erf_bf16x2(pk[j]);
+        f[2 * j] = y.x;
+        f[2 * j + 1] = y.y;
+      }
     }
   } else if (p.act == 2) {
     const bf16* ap = p.aux + static_cast<long long>(row) * p.ldaux + n;
@@ -134,10 +145,19 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, int row, int n
           w[4 * j] = u.x; w[4 * j + 1] = u.y; w[4 * j + 2] = u.z; w[4 * j + 3] = u.w;
         }
       }
+      if (p.gelu_fp32 & 2) {
 #pragma unroll
-      for (int t = 0; t < 16; ++t) {
-        f[2 * t] *= gelu_erf_grad<false>(bf16lo(w[t]));
-        f[2 * t + 1] *= gelu_erf_grad<true>(bf16hi(w[t]));
+        for (int t = 0; t < 16; ++t) {
+          f[2 * t] *= gelu_erf_grad<false>(bf16lo(w[t]));
+          f[2 * t + 1] *= gelu_erf_grad<true>(bf16hi(w[t]));
+        }
+      } else {
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          const float2 gg = gelu_erf_grad_bf16x2(w[t]);
+          f[2 * t] *= gg.x;
+          f[2 * t + 1] *= gg.y;
+        }
       }
     } else {
       _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { f[j] *= gelu_erf_grad<false>(__bfloat162float(ap[j])); }
@@ -526,8 +546,13 @@ extern "C" int vsn_gemm_bf16(const void* A, long long lda, int a_mn, const void*
     a.wide = wide ? 1 : 0;
   }
   a.rowsum = rowsum_out;
+  {
+    static int gm = -1;
+    if (gm < 0) { const char* e = getenv("VSN_GELU_FP32"); gm = e ? atoi(e) & 3 : 1; }   // default: fp32 forward, packed backward
+    a.gelu_fp32 = gm;
+  }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  int ew = ((K <= 256 || act == 2) && out_kind != 2) ? 16 : 8;
+  int ew = out_kind != 2 ? 16 : 8;   // measured: 16 epilogue warps never lose on the store/activation epilogues
   if (forced_ew() == 8 || forced_ew() == 16) ew = forced_ew();
   if (ew == 16) {
     switch (BN) {
