@@ -314,14 +314,15 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // MMA issuer: the warp runs converged (all lanes wait on the barriers), one elected lane issues
+    {
       const uint32_t idesc = tc::make_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
       const uint32_t idesc_rs = tc::make_idesc_bf16(BM, 16, p.a_mn, 0);
       const uint64_t ones_desc = tc::make_smem_desc_sw128(tc::smem_u32(ones_s), 16, 1024);
       const uint32_t a_step = p.a_mn ? 2048u : 32u;   // bytes per K=16 step
       const uint32_t b_step = p.b_mn ? 2048u : 32u;
-      const uint32_t a_lbo = p.a_mn ? 8192u : 16u;
-      const uint32_t b_lbo = p.b_mn ? 8192u : 16u;
+      const uint64_t adesc0 = tc::make_smem_desc_sw128(tc::smem_u32(smem), p.a_mn ? 8192u : 16u, 1024);
+      const uint64_t bdesc0 = tc::make_smem_desc_sw128(tc::smem_u32(smem) + A_BYTES, p.b_mn ? 8192u : 16u, 1024);
       int it = 0;
       TileCoord t;
       for (int lt = 0; cta_tile(p, lt, tiles_n, BN, t); ++lt) {
@@ -335,20 +336,33 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
           const uint32_t ph = (it / C::STAGES) & 1;
           tc::mbar_wait(&full_bar[s], ph);
           tc::fence_after_sync();
-          const uint32_t sa = tc::smem_u32(smem + s * C::STAGE_BYTES);
-          const uint32_t sb = sa + A_BYTES;
+          const uint64_t ad = tc::desc_advance(adesc0, s * C::STAGE_BYTES);
+          const uint64_t bd = tc::desc_advance(bdesc0, s * C::STAGE_BYTES);
           const int krem = p.K - (t.kb0 + i) * BK;
           const int ksteps = krem >= BK ? BK / 16 : (krem + 15) / 16;
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t ad = tc::make_smem_desc_sw128(sa + k * a_step, a_lbo, 1024);
-            const uint64_t bd = tc::make_smem_desc_sw128(sb + k * b_step, b_lbo, 1024);
-            tc::mma_bf16_ss(d, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
-            // row sums of A on the tensor cores: one N=16 MMA against the all-ones tile (first n-tile only)
-            if (do_rs) tc::mma_bf16_ss(tmem_base + C::RS_COL + buf * 16, ad, ones_desc, idesc_rs, (i > 0 || k > 0) ? 1u : 0u);
+          if (tc::elect_one()) {
+            if (ksteps == BK / 16) {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                tc::mma_bf16_ss(d, tc::desc_advance(ad, k * a_step), tc::desc_advance(bd, k * b_step), idesc,
+                                (i > 0 || k > 0) ? 1u : 0u);
+                // row sums of A on the tensor cores: one N=16 MMA against the all-ones tile (first n-tile only)
+                if (do_rs) tc::mma_bf16_ss(tmem_base + C::RS_COL + buf * 16, tc::desc_advance(ad, k * a_step), ones_desc,
+                                           idesc_rs, (i > 0 || k > 0) ? 1u : 0u);
+              }
+            } else {
+              for (int k = 0; k < ksteps; ++k) {
+                tc::mma_bf16_ss(d, tc::desc_advance(ad, k * a_step), tc::desc_advance(bd, k * b_step), idesc,
+                                (i > 0 || k > 0) ? 1u : 0u);
+                if (do_rs) tc::mma_bf16_ss(tmem_base + C::RS_COL + buf * 16, tc::desc_advance(ad, k * a_step), ones_desc,
+                                           idesc_rs, (i > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+            tc::mma_commit(&empty_bar[s]);                       // frees the smem stage once these MMAs retire
+            if (i == t.nkb - 1) tc::mma_commit(&acc_full[buf]);  // accumulator complete
           }
-          tc::mma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs retire
+          __syncwarp();
         }
-        tc::mma_commit(&acc_full[buf]);    // accumulator complete
       }
     }
   } else {

@@ -48,11 +48,24 @@ class MultiTensorTable:
         self.chunk_off = torch.tensor(co, dtype=torch.int64, device=self.device)
 
     def ptr_array(self, tensors: Sequence[torch.Tensor]) -> torch.Tensor:
+        """Device array of the tensors' addresses.  Uploaded from a pinned staging ring with a non-blocking copy:
+        a `torch.tensor(list, device=...)` would copy from pageable memory, which waits for all queued GPU work --
+        a hidden device synchronisation every time gradients are re-allocated (e.g. after zero_grad(set_to_none))."""
         assert len(tensors) == self.n
         for t, n in zip(tensors, self.sizes_host):
             if t.numel() != n or not t.is_contiguous() or not t.is_cuda:
                 raise RuntimeError("multi-tensor kernels need contiguous CUDA tensors of matching sizes")
-        return torch.tensor([t.data_ptr() for t in tensors], dtype=torch.int64, device=self.device)
+        if not hasattr(self, "_stage"):
+            self._stage = [(torch.empty(self.n, dtype=torch.int64).pin_memory(), torch.cuda.Event()) for _ in range(4)]
+            self._stage_i = 0
+        host, ev = self._stage[self._stage_i]
+        self._stage_i = (self._stage_i + 1) % len(self._stage)
+        ev.synchronize()                                   # the copy that last used this staging buffer is done
+        host.copy_(torch.tensor([t.data_ptr() for t in tensors], dtype=torch.int64))
+        dev = torch.empty(self.n, dtype=torch.int64, device=self.device)
+        dev.copy_(host, non_blocking=True)
+        ev.record(torch.cuda.current_stream(self.device))
+        return dev
 
     def _tab(self):
         return self.sizes.data_ptr(), self.chunk_tensor.data_ptr(), self.chunk_off.data_ptr(), self.n_chunks
