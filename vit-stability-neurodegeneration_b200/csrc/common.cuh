@@ -168,8 +168,7 @@ __device__ __forceinline__ float2 gelu_erf_grad_bf16x2(uint32_t pk) {
   const __half2 cdf = h2_from_u32((h2_to_u32(he) & m) | (hi & ~m));
   const __half2 axc = __hmin2(ax, __float2half2_rn(8.0f));                          // phi(8) ~ 5e-15
   const __half2 g = h2_from_u32(h2_ex2(h2_to_u32(__hmul2(__hmul2(axc, axc), __float2half2_rn(-0.72134752f)))));
-  const float2 c = __half22float2(cdf), gg = __half22float2(g), xf = __half22float2(x);
-  return make_float2(fmaf(xf.x * 0.39894228f, gg.x, c.x), fmaf(xf.y * 0.39894228f, gg.y, c.y));
+  return __half22float2(__hfma2(__hmul2(x, __float2half2_rn(0.39894228f)), g, cdf));
 }
 
 // 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): a thread that owns a contiguous run of a row reads or
