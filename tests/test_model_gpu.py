@@ -136,3 +136,37 @@ def test_vit3c_full_size_seed0_logits():
     with torch.no_grad():
         z = model(x3.cuda())[0]
     assert rel_err(z, full["vit3c_seed0_in144x160x144"]) < TOL
+
+
+def test_in_kernel_gradient_accumulation_matches_autograd():
+    """TrainStep sums the block gradients of an optimiser step's micro-batches inside the kernels
+    (swin.GradAccumulation) and releases them to autograd once; same result as autograd's per-parameter adds."""
+    swin_model, _ = _models()
+    from vsn_b200 import swin
+    from vsn_b200.train import TrainStep, soft_target_ce
+    case = SWIN_CASES["swin_small_even"]
+    model = swin_model.SwinTransformerT(**swin_ctor_kwargs(case)).cuda().train()
+    _load_synth(model, meta()["swin_small_even"]["state_shapes"])
+    xs = [torch.from_numpy(synth_volume(case["input"], seed=10 + i)).cuda() for i in range(3)]
+    ys = [torch.from_numpy(synth_targets(xs[0].shape[0], case["num_classes"], seed=20 + i)).cuda() for i in range(3)]
+    nblk = sum(case["depths"])
+
+    def run(in_kernel):
+        model.zero_grad(set_to_none=True)
+        masks = synth_keep_masks(3 * max(2 * (nblk - 1), 1), xs[0].shape[0], keep=0.7, seed=5)
+        swin_model.DropPath.forced_masks = iter(torch.from_numpy(mm) for mm in masks)
+        try:
+            if in_kernel:
+                ts = TrainStep(model, use_ema=False)
+                ts._accumulate(list(zip(xs, ys)))
+            else:
+                for x, y in zip(xs, ys):
+                    (soft_target_ce(model(x), y, 0.1) / 3).backward()
+        finally:
+            swin_model.DropPath.forced_masks = None
+        assert not swin.GradAccumulation.store and not swin.GradAccumulation.active
+        return {k: p.grad.clone() for k, p in model.named_parameters()}
+
+    ref, got = run(False), run(True)
+    for k in ref:
+        assert rel_err(got[k], ref[k]) < 1e-4, k

@@ -957,8 +957,11 @@ __global__ void __launch_bounds__(256) wattn_delta_kernel(const WinAttnArgs p, f
   constexpr int N = WD * WH * WW;
   const int s = blockIdx.x;
   const WinCoord wc = win_coord(p, s, WD, WH, WW);
-  for (int item = threadIdx.x; item < N * p.heads; item += blockDim.x) {
-    const int head = item % p.heads, i = item / p.heads;
+  // blockIdx.y takes a slice of the heads so that launches with few windows (late stages) still fill the chip
+  const int hp = (p.heads + gridDim.y - 1) / gridDim.y, h0 = blockIdx.y * hp;
+  const int nh = min(hp, p.heads - h0);
+  for (int item = threadIdx.x; item < N * nh; item += blockDim.x) {
+    const int head = h0 + item % nh, i = item / nh;
     const TokenGeom g = token_geom_w<WD, WH, WW>(p, wc, i);
     const uint4* o = reinterpret_cast<const uint4*>(p.out + static_cast<long long>(g.row) * p.C + head * HD);
     const uint4* d = reinterpret_cast<const uint4*>(p.dout + static_cast<long long>(g.row) * p.C + head * HD);
@@ -989,7 +992,13 @@ int wattn_tc_bwd(const WinAttnArgs& a, float* delta, cudaStream_t stream) {
     VSN_CUDA(cudaFuncSetAttribute(wattn_bwd_kernel<6, 7, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     attr_set = true;
   }
-  wattn_delta_kernel<6, 7, 6><<<a.S, 256, 0, stream>>>(a, delta);
+  {
+    int ys = ceil_div(2 * vsn_num_sms(), a.S);
+    if (ys > a.heads) ys = a.heads;
+    if (ys < 1) ys = 1;
+    ys = ceil_div(a.heads, ceil_div(a.heads, ys));      // no empty slices
+    wattn_delta_kernel<6, 7, 6><<<dim3(a.S, ys), 256, 0, stream>>>(a, delta);
+  }
   VSN_LAUNCH_CHECK();
   int groups = vsn_num_sms() / (2 * a.heads);
   if (groups < 1) groups = 1;

@@ -63,6 +63,36 @@ class WeightShadow:
 
 
 # --------------------------------------------------------------------------------------
+# gradient accumulation over micro-batches inside the kernels
+# --------------------------------------------------------------------------------------
+class GradAccumulation:
+    """Every parameter-gradient kernel of the path accumulates (+=).  Inside `with GradAccumulation.over(n)` the
+    block Functions keep ONE set of gradient buffers per block for all the micro-batches of an optimiser step and
+    hand them to autograd only on the last one: the non-final backward passes return no parameter gradients, so
+    autograd launches no per-parameter `grad += new` kernels, and the data-parallel hooks fire exactly once, when
+    the sums are complete (the same moment `DistributedDataParallel.no_sync()` would release them,
+    train/train_transformer.py:1131-1137).  Outside the context every backward returns its gradients as usual."""
+
+    active = False
+    final = True
+    store: dict = {}
+
+    @classmethod
+    def begin(cls, final: bool) -> None:
+        cls.active, cls.final = True, final
+
+    @classmethod
+    def end(cls) -> None:
+        cls.active, cls.final = False, True
+        if not cls.store:
+            return
+        left = len(cls.store)
+        cls.store.clear()
+        raise RuntimeError(f"GradAccumulation: {left} blocks were left with unreleased gradients "
+                           "(the last micro-batch must run with final=True)")
+
+
+# --------------------------------------------------------------------------------------
 # per-unit autograd Functions
 # --------------------------------------------------------------------------------------
 @dataclass
@@ -76,6 +106,17 @@ class BlockCfg:
     w16: Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor] = None   # qkv, proj, fc1, fc2 (bf16)
     scale1: Optional[torch.Tensor] = None   # DropPath keep/(1-p) per sample for the attention branch
     scale2: Optional[torch.Tensor] = None   # ... for the MLP branch
+    acc_key: int = 0                        # identity of the block (key of its GradAccumulation buffers)
+    # backward side channel: the block that consumes this block's input gradient (the previous block of the stage)
+    # starts by casting it to bf16 scaled by ITS MLP DropPath factor; when `emit_for_prev` is set this block's last
+    # LayerNorm-backward kernel writes that bf16 copy as a second output and `take_from_next` tells the consumer to
+    # pick it up instead of running the cast kernel (saves one read of the fp32 gradient and a launch per block).
+    emit_for_prev: bool = False
+    prev_scale2: Optional[torch.Tensor] = None
+    take_from_next: bool = False
+
+
+_SIDE: dict = {}     # fp32 gradient data_ptr -> its bf16 copy pre-scaled for the consuming block (see BlockCfg)
 
 
 class SwinBlockFn(torch.autograd.Function):
@@ -123,11 +164,22 @@ class SwinBlockFn(torch.autograd.Function):
         shapes = [*ctx.shapes, (ctx.shapes[0][0],), (C,), (w1.shape[0],), (C,), (C,), (C,), (C,), (C,)]
         if table is not None:
             shapes.append(tuple(table.shape))
+        acc = GradAccumulation
+        bufs = acc.store.get(cfg.acc_key) if acc.active else None
+        if bufs is None:
+            bufs = zeros_like_shapes(shapes, dev)
+            if acc.active and not acc.final:
+                acc.store[cfg.acc_key] = bufs
+        elif acc.final:
+            del acc.store[cfg.acc_key]
+        release = not acc.active or acc.final            # hand the gradients to autograd in this pass?
         (d_qkv_w, d_proj_w, d_fc1_w, d_fc2_w, d_qkv_b, d_proj_b, d_fc1_b, d_fc2_b, d_n1w, d_n1b, d_n2w, d_n2b,
-         *rest) = zeros_like_shapes(shapes, dev)
+         *rest) = bufs
         d_table = rest[0] if table is not None else None
         # ---- MLP branch: x2 = x1 + s2 * (W2 gelu(W1 LN2(x1) + b1) + b2)
-        gs = ops.cast_rows_bf16(g, cfg.scale2, tps)
+        gs = _SIDE.pop(g.data_ptr(), None) if cfg.take_from_next else None
+        if gs is None or gs.shape != g.shape:
+            gs = ops.cast_rows_bf16(g, cfg.scale2, tps)
         ops.linear_wgrad(gs, a, d_fc2_w, dbias=d_fc2_b)
         dh = ops.linear_dgrad(gs, w2, gelu_aux=h)
         ops.linear_wgrad(dh, y2, d_fc1_w, dbias=d_fc1_b)
@@ -141,7 +193,13 @@ class SwinBlockFn(torch.autograd.Function):
                             table=table, dtable=d_table)
         ops.linear_wgrad(dqkv, y1, d_qkv_w, dbias=d_qkv_b if ctx.has_qkv_bias else None)
         dy1 = ops.linear_dgrad(dqkv, wq)
-        g0, _ = ops.layernorm_bwd(dy1, x, mean1, rstd1, n1w, resid_grad=g1, dx_out=g1, dgamma=d_n1w, dbeta=d_n1b)
+        g0, g0b = ops.layernorm_bwd(dy1, x, mean1, rstd1, n1w, resid_grad=g1, dx_out=g1, dgamma=d_n1w, dbeta=d_n1b,
+                                    want_bf16=cfg.emit_for_prev, row_scale=cfg.prev_scale2, rows_per_group=tps)
+        if cfg.emit_for_prev:
+            _SIDE.clear()                       # at most one pending hand-over
+            _SIDE[g0.data_ptr()] = g0b
+        if not release:
+            return (g0,) + (None,) * 14
         return (g0, d_n1w, d_n1b, d_qkv_w, d_qkv_b if ctx.has_qkv_bias else None, d_table, d_proj_w, d_proj_b,
                 d_n2w, d_n2b, d_fc1_w, d_fc1_b, d_fc2_w, d_fc2_b, None)
 

@@ -228,14 +228,21 @@ class SwinTransformer3DBackbone(nn.Module):
             if pdims != real:
                 t = swin.GridCopyFn.apply(t, real, pdims, B)
             tps = pdims[0] * pdims[1] * pdims[2]
+            prev_cfg = None
             for blk in layer.blocks:
                 shifted = any(s > 0 for s in blk.shift_size)
                 geom = ops.WindowGeom(B, pdims, blk.window_size, blk.shift_size if shifted else (0, 0, 0), shifted)
                 p = blk.drop_path.drop_prob if isinstance(blk.drop_path, DropPath) else 0.0
                 cfg = swin.BlockCfg(heads=blk.num_heads, hd=C // blk.num_heads, geom=geom, tokens_per_sample=tps,
+                                    acc_key=id(blk),
                                     w16=tuple(self._shadow.view(wi + j) for j in range(4)),
                                     scale1=swin.droppath_scale(p, B, t.device, self.training, forced),
                                     scale2=swin.droppath_scale(p, B, t.device, self.training, forced))
+                if prev_cfg is not None:
+                    # backward hand-over of the bf16 input gradient from this block to the previous one
+                    cfg.emit_for_prev, cfg.prev_scale2 = True, prev_cfg.scale2
+                    prev_cfg.take_from_next = True
+                prev_cfg = cfg
                 wi += 4
                 a = blk.attn
                 t = swin.SwinBlockFn.apply(t, blk.norm1.weight, blk.norm1.bias, a.qkv.weight, a.qkv.bias,

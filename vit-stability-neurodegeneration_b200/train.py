@@ -52,8 +52,10 @@ class TrainStep:
     def _accumulate(self, batches: Sequence[Tuple[torch.Tensor, torch.Tensor]]) -> torch.Tensor:
         n = len(batches)
         total = None
+        from .swin import GradAccumulation
         for i, (x, y) in enumerate(batches):
             last = i == n - 1
+            GradAccumulation.begin(final=last)           # block gradients are summed in-kernel over the micro-batches
             if self.grad_sync is not None:
                 ctx = nullcontext() if last else self.grad_sync.no_sync()
             else:
@@ -62,6 +64,7 @@ class TrainStep:
                 loss = soft_target_ce(self.model(x), y, self.smoothing) / n
                 loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
+        GradAccumulation.end()
         if self.grad_sync is not None:
             self.grad_sync.finish()               # gradients are now the cross-rank mean
         return total

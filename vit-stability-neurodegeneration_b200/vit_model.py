@@ -150,7 +150,7 @@ class ViT(nn.Module):
         for layer in self.transformer.layers:
             attn, ff, dp = layer[0], layer[1], layer[4]
             p = dp.drop_prob if isinstance(dp, DropPath) else 0.0
-            cfg = swin.BlockCfg(heads=attn.heads, hd=attn.dim_head, geom=None, tokens_per_sample=N, S=B, N=N,
+            cfg = swin.BlockCfg(heads=attn.heads, hd=attn.dim_head, geom=None, tokens_per_sample=N, S=B, N=N, acc_key=id(attn),
                                 w16=tuple(self._shadow.view(wi + j) for j in range(4)),
                                 scale1=swin.droppath_scale(p, B, t.device, self.training, forced),
                                 scale2=swin.droppath_scale(p, B, t.device, self.training, forced))
