@@ -148,7 +148,8 @@ template <int WD, int WH, int WW>
 struct FwdSmem {
   static constexpr int BIAS = FWD_STAGES * STAGE_BYTES;
   static constexpr int KEYCODE = BIAS + BiasTab<WD, WH, WW>::BYTES;
-  static constexpr int STATS = KEYCODE + FWD_STAGES * NP;      // float2 [2][4 parts][128]
+  static constexpr int ROWIDX = KEYCODE + FWD_STAGES * NP;     // int [2][256] source row of every token + [2] masked flag
+  static constexpr int STATS = ROWIDX + FWD_STAGES * NP * 4 + 16;   // float2 [2][4 parts][128]
   static constexpr int BARS = STATS + 2 * 4 * 128 * 8;
   static constexpr int TOTAL = BARS + 24 * 8;
 };
@@ -198,6 +199,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
   uint8_t* stages = smem;
   uint8_t* bias_s = smem + SM::BIAS;
   uint8_t* keycode = smem + SM::KEYCODE;
+  int* rowidx = reinterpret_cast<int*>(smem + SM::ROWIDX);        // written by the loader with the tiles
+  int* winmask = rowidx + FWD_STAGES * NP;
   float2* stats = reinterpret_cast<float2*>(smem + SM::STATS);    // (local max, local sum)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::BARS);
   uint64_t* qkv_full = bars;        // [2] loader lanes -> MMA
@@ -223,9 +226,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
       tc::mbar_init(&qkv_full[i], 32);
       tc::mbar_init(&qkv_empty[i], 1);
       tc::mbar_init(&s_full[i], 1);
-      tc::mbar_init(&p_ready[i], SM_WARPS * 32);
+      tc::mbar_init(&p_ready[i], SM_WARPS * 16);   // one group of 8 warps per query half
       tc::mbar_init(&o_full[i], 1);
-      tc::mbar_init(&o_read[i], SM_WARPS * 32);
+      tc::mbar_init(&o_read[i], SM_WARPS * 16);
     }
     for (int i = 0; i < 8; ++i) tc::mbar_init(&st_full[i], 128);
     tc::fence_barrier_init();
@@ -256,6 +259,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
       for (int i = lane; i < N; i += 32) {
         const TokenGeom g = token_geom_w<WD, WH, WW>(p, wc, i);
         keycode[st * NP + i] = static_cast<uint8_t>(g.code);
+        rowidx[st * NP + i] = g.row;
         const bf16* src = p.qkv + g.row * ld + head * HD;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -265,6 +269,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
           tc::cp_async16(sq + 2 * TILE_BYTES + o, src + 2 * p.C + c * 8);
         }
       }
+      if (lane == 0) winmask[st] = wc.masked() ? 1 : 0;
       tc::cp_async_wait_all();
       tc::fence_proxy_async();
       tc::mbar_arrive(&qkv_full[st]);
@@ -312,20 +317,97 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
     }
   } else {
     // ------------------------------------------------------------------ softmax + epilogue
-    // Thread = (TMEM lane rl, column part): 64 of the row's 256 logits, exponentiated against the LOCAL max of
-    // those 64 (no cross-thread exchange on the critical path).  P V is accumulated per part; the epilogue
-    // of unit u (run inside unit u+1, once O is ready) rescales the four partial outputs to the row max.
-    const int q4 = warp & 3, part = warp >> 2;
+    // Two independent groups of 8 warps: group g owns the query half h = g of every window (its own TMEM region,
+    // its own barriers), so while one group waits for its MMAs (P V, then the next S) the other one keeps the
+    // MUFU / FMA pipes busy -- the groups run half a period apart instead of all 16 warps in lock step.
+    // Thread = (TMEM lane rl, column half ch): two sequential passes over 64 of the row's 256 logits each
+    // (part = 2*pass + ch), exponentiated against the LOCAL max of those 64 (no cross-thread exchange on the
+    // critical path).  P V is accumulated per part; the epilogue rescales the four partial outputs to the row max.
+    const int h = warp >> 3, q4 = warp & 3, ch = (warp >> 2) & 1;
     const int rl = q4 * 32 + lane;
+    const int i = h * 128 + rl;
+    const int ib = i < N ? i : N - 1;
+    const int rowbase = BT::rowbase(ib);
     const uint32_t lane_addr = static_cast<uint32_t>(q4 * 32) << 16;
+    const uint32_t region = tmem_base + lane_addr + h * NP;
     const float cscale = p.scale * LOG2E;
-    WinCoord wc_cur = {}, wc_prev = {};     // window of the current unit / of the unit whose epilogue is pending
 
-    auto epilogue = [&](int v) {
-      const int h = v & 1;
-      const int s = blockIdx.x + (v >> 1) * gridDim.x;
-      const int i = h * 128 + rl;
-      tc::mbar_wait(&st_full[q4 * 2 + h], (v >> 1) & 1);
+    for (int it = 0; it < n_it; ++it) {
+      const int st = it & 1;
+      const int s = blockIdx.x + it * gridDim.x;
+
+      tc::mbar_wait(&s_full[h], it & 1);
+      tc::fence_after_sync();
+      // geometry of the window as the loader worked it out (stage st is not refilled before this unit's P V ran)
+      const uint32_t cq4 = static_cast<uint32_t>(keycode[st * NP + ib]) * 0x01010101u;
+      const int out_row = rowidx[st * NP + ib];
+      const bool masked = winmask[st] != 0;
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        const int part = 2 * pass + ch;
+        uint32_t x[64];
+        tc::tmem_ld_32x32b_x32(region + part * 64, x);
+        tc::tmem_ld_32x32b_x32(region + part * 64 + 32, x + 32);
+        tc::tmem_ld_wait();
+        // P of part 1 (this quadrant's other warp) lands on the upper half of part 0's logits and P of part 2 on
+        // part 1's: both loads of pass 0 must have completed before either warp stores
+        if (pass == 0) tc::named_bar_sync(1 + h * 4 + q4, 64);
+        if (pass == 0) {
+          if (ch == 0) add_bias<WD, WH, WW, 0>(x, bias_s, rowbase, cscale);
+          else add_bias<WD, WH, WW, 1>(x, bias_s, rowbase, cscale);
+        } else {
+          if (ch == 0) add_bias<WD, WH, WW, 2>(x, bias_s, rowbase, cscale);
+          else add_bias<WD, WH, WW, 3>(x, bias_s, rowbase, cscale);
+        }
+        if (masked) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint4 kc = *reinterpret_cast<const uint4*>(keycode + st * NP + part * 64 + c * 16);
+            const uint32_t kw[4] = {kc.x, kc.y, kc.z, kc.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const uint32_t ne = __vcmpne4(kw[t], cq4);
+#pragma unroll
+              for (int b = 0; b < 4; ++b) {
+                const uint32_t m32 = __byte_perm(ne, 0, 0x8888u | (0x1111u * b));
+                const int k = c * 16 + t * 4 + b;
+                x[k] = __float_as_uint(__uint_as_float(x[k]) + __uint_as_float(m32 & __float_as_uint(MASK_L2E)));
+              }
+            }
+          }
+        }
+        float mx0 = -3.0e38f, mx1 = -3.0e38f;
+#pragma unroll
+        for (int k = 0; k < 64; k += 4) {
+          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(x[k]), __uint_as_float(x[k + 1])));
+          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(x[k + 2]), __uint_as_float(x[k + 3])));
+        }
+        // a part made only of padded keys / masked-out keys keeps a finite reference
+        const float m = fmaxf(fmaxf(mx0, mx1), -20000.f);
+
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; k += 2) {
+          // VAR&1: 1 of 4 exponentials on the FMA pipe instead of the MUFU pipe
+          const float p0 = tc::ex2_approx(__uint_as_float(x[2 * k]) - m);
+          const float p1 = (VAR & 1) ? exp2_poly(__uint_as_float(x[2 * k + 1]) - m) : tc::ex2_approx(__uint_as_float(x[2 * k + 1]) - m);
+          const float p2 = tc::ex2_approx(__uint_as_float(x[2 * k + 2]) - m);
+          const float p3 = tc::ex2_approx(__uint_as_float(x[2 * k + 3]) - m);
+          l0 += p0 + p1;
+          l1 += p2 + p3;
+          x[k] = pack_bf16(p0, p1);
+          x[k + 1] = pack_bf16(p2, p3);
+        }
+        tc::tmem_st_32x32b_x32(region + part * 32, x);
+        stats[h * 512 + part * 128 + rl] = make_float2(m, l0 + l1);
+        tc::mbar_arrive(&st_full[q4 * 2 + h]);
+      }
+      tc::tmem_st_wait();
+      tc::fence_before_sync();
+      tc::mbar_arrive(&p_ready[h]);
+
+      // ---- epilogue of this unit: combine the four partial outputs (16 of the 32 output columns per thread)
+      tc::mbar_wait(&st_full[q4 * 2 + h], it & 1);
       const float2* sp = stats + h * 512 + rl;
       const float2 s0 = sp[0], s1 = sp[128], s2 = sp[256], s3 = sp[384];
       const float m = fmaxf(fmaxf(s0.x, s1.x), fmaxf(s2.x, s3.x));
@@ -333,114 +415,40 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
       const float w2 = tc::ex2_approx(s2.x - m), w3 = tc::ex2_approx(s3.x - m);
       const float l = fmaf(w0, s0.y, fmaf(w1, s1.y, fmaf(w2, s2.y, w3 * s3.y)));
       const float inv = 1.f / l;
-      tc::mbar_wait(&o_full[h], (v >> 1) & 1);
+      tc::mbar_wait(&o_full[h], it & 1);
       tc::fence_after_sync();
-      const uint32_t ob = tmem_base + lane_addr + h * NP + 128 + part * 8;
-      float r[8];
+      const uint32_t ob = region + 128 + ch * 16;
+      float r[16];
       {
-        uint32_t o[8];
-        tc::tmem_ld_32x32b_x8(ob, o);
+        uint32_t o[16];
+        tc::tmem_ld_32x32b_x16(ob, o);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 8; ++k) r[k] = w0 * __uint_as_float(o[k]);
-        tc::tmem_ld_32x32b_x8(ob + 32, o);
+        for (int k = 0; k < 16; ++k) r[k] = w0 * __uint_as_float(o[k]);
+        tc::tmem_ld_32x32b_x16(ob + 32, o);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 8; ++k) r[k] = fmaf(w1, __uint_as_float(o[k]), r[k]);
-        tc::tmem_ld_32x32b_x8(ob + 64, o);
+        for (int k = 0; k < 16; ++k) r[k] = fmaf(w1, __uint_as_float(o[k]), r[k]);
+        tc::tmem_ld_32x32b_x16(ob + 64, o);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 8; ++k) r[k] = fmaf(w2, __uint_as_float(o[k]), r[k]);
-        tc::tmem_ld_32x32b_x8(ob + 96, o);
+        for (int k = 0; k < 16; ++k) r[k] = fmaf(w2, __uint_as_float(o[k]), r[k]);
+        tc::tmem_ld_32x32b_x16(ob + 96, o);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 8; ++k) r[k] = fmaf(w3, __uint_as_float(o[k]), r[k]) * inv;
+        for (int k = 0; k < 16; ++k) r[k] = fmaf(w3, __uint_as_float(o[k]), r[k]) * inv;
       }
       tc::fence_before_sync();
       tc::mbar_arrive(&o_read[h]);
       if (i < N) {
-        const TokenGeom g = token_geom_w<WD, WH, WW>(p, wc_prev, i);
-        uint4 w;
-        w.x = pack_bf16(r[0], r[1]); w.y = pack_bf16(r[2], r[3]); w.z = pack_bf16(r[4], r[5]); w.w = pack_bf16(r[6], r[7]);
-        *reinterpret_cast<uint4*>(p.out + static_cast<long long>(g.row) * p.C + head * HD + part * 8) = w;
+        uint32_t w[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w[k] = pack_bf16(r[2 * k], r[2 * k + 1]);
+        st_global_v8(p.out + static_cast<long long>(out_row) * p.C + head * HD + ch * 16, w);
       }
-      if (part == 0 && p.lse != nullptr)
+      if (ch == 0 && p.lse != nullptr)
         p.lse[(static_cast<long long>(s) * p.heads + head) * NP + i] = m + log2f(l);   // log2 domain (consumed by wattn_bwd_kernel)
-    };
-
-    for (int u = 0; u < U; ++u) {
-      const int it = u >> 1, h = u & 1, st = it & 1;
-      const int s = blockIdx.x + it * gridDim.x;
-      const int i = h * 128 + rl;
-      const int ib = i < N ? i : N - 1;
-      const int rowbase = BT::rowbase(ib);
-      if (h == 0) wc_cur = win_coord(p, s, WD, WH, WW);     // once per window
-
-      tc::mbar_wait(&s_full[h], (u >> 1) & 1);
-      tc::fence_after_sync();
-      uint32_t x[64];
-      const uint32_t sbase = tmem_base + lane_addr + h * NP + part * 64;
-      tc::tmem_ld_32x32b_x32(sbase, x);
-      tc::tmem_ld_32x32b_x32(sbase + 32, x + 32);
-      tc::tmem_ld_wait();
-      if (!(VAR & 4)) switch (part) {
-        case 0: add_bias<WD, WH, WW, 0>(x, bias_s, rowbase, cscale); break;
-        case 1: add_bias<WD, WH, WW, 1>(x, bias_s, rowbase, cscale); break;
-        case 2: add_bias<WD, WH, WW, 2>(x, bias_s, rowbase, cscale); break;
-        default: add_bias<WD, WH, WW, 3>(x, bias_s, rowbase, cscale); break;
-      }
-      if (wc_cur.masked()) {
-        const uint32_t cq4 = static_cast<uint32_t>(token_geom_w<WD, WH, WW>(p, wc_cur, ib).code) * 0x01010101u;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint4 kc = *reinterpret_cast<const uint4*>(keycode + st * NP + part * 64 + c * 16);
-          const uint32_t kw[4] = {kc.x, kc.y, kc.z, kc.w};
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const uint32_t ne = __vcmpne4(kw[t], cq4);
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              const uint32_t m32 = __byte_perm(ne, 0, 0x8888u | (0x1111u * b));
-              const int k = c * 16 + t * 4 + b;
-              x[k] = __float_as_uint(__uint_as_float(x[k]) + __uint_as_float(m32 & __float_as_uint(MASK_L2E)));
-            }
-          }
-        }
-      }
-      float mx0 = -3.0e38f, mx1 = -3.0e38f;
-#pragma unroll
-      for (int k = 0; k < 64; k += 4) {
-        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(x[k]), __uint_as_float(x[k + 1])));
-        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(x[k + 2]), __uint_as_float(x[k + 3])));
-      }
-      // a part made only of padded keys / masked-out keys keeps a finite reference
-      const float m = fmaxf(fmaxf(mx0, mx1), -20000.f);
-
-      float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-      for (int k = 0; k < 32; k += 2) {
-        // the epilogue of the previous unit sits in the middle of the exponentials: by then its O is ready
-        // and only half of the logits are still live in registers
-        if (k == 16 && u > 0) epilogue(u - 1);     // wc_prev = window of unit u-1
-        // VAR&1: 1 of 4 exponentials on the FMA pipe instead of the MUFU pipe
-        const float p0 = (VAR & 2) ? (__uint_as_float(x[2 * k]) - m) : tc::ex2_approx(__uint_as_float(x[2 * k]) - m);
-        const float p1 = (VAR & 2) ? (__uint_as_float(x[2 * k + 1]) - m) : (VAR & 1) ? exp2_poly(__uint_as_float(x[2 * k + 1]) - m) : tc::ex2_approx(__uint_as_float(x[2 * k + 1]) - m);
-        const float p2 = (VAR & 2) ? (__uint_as_float(x[2 * k + 2]) - m) : tc::ex2_approx(__uint_as_float(x[2 * k + 2]) - m);
-        const float p3 = (VAR & 2) ? (__uint_as_float(x[2 * k + 3]) - m) : tc::ex2_approx(__uint_as_float(x[2 * k + 3]) - m);
-        l0 += p0 + p1;
-        l1 += p2 + p3;
-        x[k] = pack_bf16(p0, p1);
-        x[k + 1] = pack_bf16(p2, p3);
-      }
-      tc::tmem_st_32x32b_x32(tmem_base + lane_addr + h * NP + part * 32, x);
-      stats[h * 512 + part * 128 + rl] = make_float2(m, l0 + l1);
-      tc::mbar_arrive(&st_full[q4 * 2 + h]);
-      tc::tmem_st_wait();
-      tc::fence_before_sync();
-      tc::mbar_arrive(&p_ready[h]);
-      wc_prev = wc_cur;
     }
-    if (U > 0) epilogue(U - 1);
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -469,19 +477,15 @@ int wattn_tc_fwd(const WinAttnArgs& a, cudaStream_t stream) {
   using SM = FwdSmem<6, 7, 6>;
   static int var = -1;
   if (var < 0) {
+    // VSN_WATTN_VARIANT (measurements only): 0 = every exponential on the MUFU pipe, 1 = one of four on the FMA
+    // pipe (polynomial)
     const char* e = getenv("VSN_WATTN_VARIANT");
-    var = e ? atoi(e) & 7 : 0;
+    var = e ? atoi(e) & 1 : 0;
     VSN_CUDA(cudaFuncSetAttribute(wattn_fwd_kernel<6, 7, 6, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     VSN_CUDA(cudaFuncSetAttribute(wattn_fwd_kernel<6, 7, 6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
-    VSN_CUDA(cudaFuncSetAttribute(wattn_fwd_kernel<6, 7, 6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
-    VSN_CUDA(cudaFuncSetAttribute(wattn_fwd_kernel<6, 7, 6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
-    VSN_CUDA(cudaFuncSetAttribute(wattn_fwd_kernel<6, 7, 6, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
   }
   dim3 grid(groups_for(a.S, a.heads), a.heads);
   if (var == 1) wattn_fwd_kernel<6, 7, 6, 1><<<grid, FWD_THREADS, SM::TOTAL, stream>>>(a);
-  else if (var == 2) wattn_fwd_kernel<6, 7, 6, 2><<<grid, FWD_THREADS, SM::TOTAL, stream>>>(a);
-  else if (var == 4) wattn_fwd_kernel<6, 7, 6, 4><<<grid, FWD_THREADS, SM::TOTAL, stream>>>(a);
-  else if (var == 6) wattn_fwd_kernel<6, 7, 6, 6><<<grid, FWD_THREADS, SM::TOTAL, stream>>>(a);
   else wattn_fwd_kernel<6, 7, 6, 0><<<grid, FWD_THREADS, SM::TOTAL, stream>>>(a);
   VSN_LAUNCH_CHECK();
   return 0;
