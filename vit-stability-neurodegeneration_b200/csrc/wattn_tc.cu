@@ -5,15 +5,16 @@
 // most 252 tokens (padded to 256 inside the SM) -- every stage of the shipped Swin configs.
 //
 // Forward, one persistent CTA per (head, group of windows):
-//   smem   dense bias tile B[i][j] = table[rpi[i,j], head] * log2(e) as bf16 (built once per CTA, 126 KB),
+//   smem   compact relative-position bias table [(da,db,w_i)][w_j] * log2(e) as bf16 (13.4 KB, built once per CTA),
 //          a 2-deep ring of {Q,K,V}[256][32] bf16 tiles in the 64-byte-swizzled UMMA layout (96 KB),
-//          per-key region codes for the shift mask.
-//   TMEM   two 256-column regions; region r holds S = Q_h K^T for one half h of the window's queries
+//          per-token region codes and source rows of the window (written by the loader with the tiles).
+//   TMEM   two 256-column regions; region h holds S = Q_h K^T for the half h of the window's queries
 //          (128 lanes x 256 fp32 columns).  The softmax warps overwrite its first 128 columns with
-//          P (bf16 pairs) which feeds the second MMA from TMEM; O = P V accumulates in columns 128..159.
-//   warps  0-7 softmax (warp w: TMEM lanes 32*(w&3).., key half w>>2; a row is shared by two threads that
-//          exchange max / sum through smem), 8 = cp.async gather of the next window (roll and
-//          window_partition are index math on the source rows), 9 = MMA issuer (one lane).
+//          P (bf16 pairs) which feeds the second MMA from TMEM; the four partial outputs O_part = P_part V
+//          (one per 64-key part, each exponentiated against its own local max) sit in columns 128..255.
+//   warps  0-15 softmax in two independent groups (group = query half: its own TMEM region and barriers, so one
+//          group computes while the other waits for its MMAs), 16 = cp.async gather of the next window (roll and
+//          window_partition are index math on the source rows), 17 = MMA issuer (converged warp, elect.sync).
 // Nothing of size N x N ever goes to HBM: no rolled copy, no mask tensor, no bias tensor, no logits.
 #include <stdlib.h>
 #include "tc.cuh"
@@ -566,8 +567,15 @@ __device__ __forceinline__ void red_add_bf16x8(bf16* addr, uint32_t a, uint32_t 
                : "memory");
 }
 
-__device__ unsigned long long* g_bwd_timing = nullptr;   // [gridDim][16] cycle counters (VSN_WATTN_TIMING=1)
+// Per-phase cycle counters of the backward kernel: compiled in with -DVSN_WATTN_TIMING (they cost a dozen registers
+// in a kernel that runs at the 96-register cap: 0.590 -> 0.565 ms at stage 0 without them), printed when the
+// environment has VSN_WATTN_TIMING=1.
+__device__ unsigned long long* g_bwd_timing = nullptr;   // [gridDim][16]
+#ifdef VSN_WATTN_TIMING
 #define TCLK() clock64()
+#else
+#define TCLK() 0ll
+#endif
 
 template <int WD, int WH, int WW>
 __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttnArgs p, const float* __restrict__ delta_g) {
