@@ -333,6 +333,17 @@ def main():
     ms_e2e = timed(step_e2e, args.steps)
     e2e_value = vols_per_step * args.steps / (ms_e2e / 1e3)
 
+    # N > 1: every rank saw different volumes, so identical weights after all these steps mean the gradient exchange
+    # delivered the same mean gradient everywhere (checked bit for bit on a fp64 checksum of all parameters)
+    in_sync = None
+    if world > 1:
+        cks = torch.stack([p.detach().double().sum() for p in model.parameters()]).sum().reshape(1)
+        allc = [torch.empty_like(cks) for _ in range(world)]
+        dist.all_gather(allc, cks)
+        in_sync = bool(all(torch.equal(c, allc[0]) for c in allc))
+        if not in_sync:
+            raise RuntimeError(f"replicas diverged: parameter checksums {[float(c) for c in allc]}")
+
     # ---- instrumented pass: per-launch CUDA-event times of every C-ABI call in one step -----------
     roofline, table = None, []
     if not args.no_profile and rank == 0:
@@ -432,7 +443,7 @@ def main():
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config_dict(args, world),
-                "clocks": clocks, "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_ms, 3),
+                "clocks": clocks, "replicas_in_sync": in_sync, "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_ms, 3),
                 "e2e": {"value": round(e2e_value, 2), "unit": "volumes/s", "h2d_bytes_per_step": int(h2d_bytes),
                         "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3)},
                 "model_tflops_per_gpu": round(step_flops / (ms / args.steps * 1e-3) / 1e12, 1),

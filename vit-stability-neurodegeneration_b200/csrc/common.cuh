@@ -91,12 +91,12 @@ __device__ __forceinline__ float erfc_half_pos(float ax) {   // 0.5 * erfc(ax / 
   q = fmaf(q, z, 0.149565667f);
   q = fmaf(q, z, 0.918361976f);
   q = fmaf(q, z, 1.62790073f);
-  return 0.5f * exp2_neg<POLY>(-z * q);
+  return exp2_neg<POLY>(fmaf(-z, q, -1.0f));               // the factor 0.5 rides in the exponent
 }
+// gelu(x) = max(x, 0) - |x| * (1 - Phi(|x|)): no select, no cancellation in either tail
 template <bool POLY = false>
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float t = x * erfc_half_pos<POLY>(fabsf(x));     // x * (1 - Phi(|x|))
-  return x < 0.f ? t : x - t;
+  return fmaf(-fabsf(x), erfc_half_pos<POLY>(fabsf(x)), fmaxf(x, 0.f));
 }
 // The cdf term uses the MUFU or the polynomial exponential (POLY); the pdf term always uses the other one,
 // so every element costs exactly one MUFU.

@@ -87,27 +87,44 @@ __device__ __forceinline__ bool cta_tile(const GemmArgs& p, int k, int tiles_n, 
 }
 
 // One 32-column chunk of an output row: v = fp32 accumulators from TMEM, bias_s = the chunk's bias in smem.
-__device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, int row, int n, float rs, const uint32_t* v,
+// MODE specialises the hot epilogues at compile time (straight-line code, no per-chunk parameter loads and uniform
+// branches); MODE 0 reads everything from the arguments:
+//   1 = bias + GELU, bf16 output + saved pre-activation, 256-bit stores, full tiles (the fc1 forward)
+//   2 = GELU' from the saved pre-activation, bf16 output, 256-bit accesses, full tiles (the fc2 dgrad)
+//   3 = bias + residual + row scale, fp32 output, 256-bit accesses, full tiles (proj / fc2 forward)
+//   4 = optional bias, bf16 output, 256-bit stores, full tiles (qkv forward, plain dgrads)
+template <int MODE>
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs& pa, int row, int n, float rs, const uint32_t* v,
                                                const float* bias_s) {
-  const int nvalid = min(32, p.N - n);
+  struct View {       // the fields the epilogue reads, constants where the mode fixes them
+    const GemmArgs& a;
+    __device__ __forceinline__ int act() const { return MODE == 1 ? 1 : MODE == 2 ? 2 : MODE >= 3 ? 0 : a.act; }
+    __device__ __forceinline__ int out_kind() const { return MODE == 3 ? 1 : MODE >= 1 ? 0 : a.out_kind; }
+    __device__ __forceinline__ bool wide() const { return MODE >= 1 ? true : a.wide != 0; }
+    __device__ __forceinline__ bool has_bias() const { return (MODE == 1 || MODE == 3) ? true : MODE == 2 ? false : a.bias != nullptr; }
+    __device__ __forceinline__ bool has_resid() const { return MODE == 3 ? true : MODE >= 1 ? false : a.resid != nullptr; }
+  };
+  const View m{pa};
+  const GemmArgs& p = pa;
+  const int nvalid = MODE >= 1 ? 32 : min(32, p.N - n);
   float f[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-  if (p.bias != nullptr) {
+  if (m.has_bias()) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       const float4 b4 = *reinterpret_cast<const float4*>(bias_s + j);   // broadcast read
       f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
     }
   }
-  if (p.act == 1) {
+  if (m.act() == 1) {
     // GELU is evaluated on the bf16-rounded pre-activation so backward (which only has the saved bf16
     // value) differentiates exactly the function forward applied; the rounding reuses the packed pairs.
     bf16* ap = p.aux + static_cast<long long>(row) * p.ldaux + n;
     uint32_t pk[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
-    if (nvalid == 32 && p.wide) {
+    if (nvalid == 32 && m.wide()) {
       st_global_v8(ap, pk);
       st_global_v8(ap + 16, pk + 8);
     } else if (nvalid == 32) {
@@ -131,11 +148,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, int row, int n
         f[2 * j + 1] = y.y;
       }
     }
-  } else if (p.act == 2) {
+  } else if (m.act() == 2) {
     const bf16* ap = p.aux + static_cast<long long>(row) * p.ldaux + n;
     if (nvalid == 32) {
       uint32_t w[16];
-      if (p.wide) {
+      if (m.wide()) {
         ld_global_v8(ap, w);
         ld_global_v8(ap + 16, w + 8);
       } else {
@@ -167,9 +184,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, int row, int n
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] *= rs;
   }
-  if (p.resid != nullptr) {
+  if (m.has_resid()) {
     const float* rp = p.resid + static_cast<long long>(row) * p.ldr + n;
-    if (nvalid == 32 && p.wide) {
+    if (nvalid == 32 && m.wide()) {
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
         uint32_t r8[8];
@@ -187,9 +204,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, int row, int n
       _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { f[j] += rp[j]; }
     }
   }
-  if (p.out_kind == 0) {
+  if (m.out_kind() == 0) {
     bf16* op = reinterpret_cast<bf16*>(p.out) + static_cast<long long>(row) * p.ldo + n;
-    if (nvalid == 32 && p.wide) {
+    if (nvalid == 32 && m.wide()) {
       uint32_t o[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) o[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
@@ -206,9 +223,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, int row, int n
     } else {
       _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { op[j] = __float2bfloat16(f[j]); }
     }
-  } else if (p.out_kind == 1) {
+  } else if (m.out_kind() == 1) {
     float* op = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + n;
-    if (nvalid == 32 && p.wide) {
+    if (nvalid == 32 && m.wide()) {
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
         uint32_t o[8];
@@ -242,7 +259,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, int row, int n
 // EW = number of epilogue warps (8 or 16).  Small-K problems are bound by the epilogue (one MUFU + ~25 FP32
 // instructions per element for the GELU variants, the stores for the others), so they run 16 epilogue warps
 // (4 per scheduler) to hide latency; large-K problems keep 8 with software-pipelined TMEM loads.
-template <int BN, int EW>
+template <int BN, int EW, int MODE>
 __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                   const __grid_constant__ CUtensorMap tmB,
                                                                   const GemmArgs p) {
@@ -380,7 +397,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
       // Stationary schedule: staged once, the column never changes; otherwise once per tile into the buffer
       // whose previous readers finished two tiles ago.
       float* bs = bias_s + (p.stationary ? 0 : buf * 256);
-      if (p.bias != nullptr && (lt == 0 || !p.stationary)) {
+      if ((MODE == 1 || MODE == 3 || (MODE != 2 && p.bias != nullptr)) && (lt == 0 || !p.stationary)) {
         if (et < BN) bs[et] = (t.n0 + et < p.N) ? p.bias[t.n0 + et] : 0.f;
         tc::named_bar_sync(1, EPI_THREADS);
       }
@@ -402,7 +419,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
             tc::tmem_ld_wait();
             if (c0 + NPAR * 32 < BN) tc::tmem_ld_32x32b_x32(tb + c0 + NPAR * 32, v[(i + 1) & 1]);
             const int n = t.n0 + c0;
-            if (row_ok && n < p.N) epilogue_chunk(p, row, n, rs, v[i & 1], bs + c0);
+            if (row_ok && n < p.N) epilogue_chunk<MODE>(p, row, n, rs, v[i & 1], bs + c0);
           }
         }
       } else {
@@ -412,7 +429,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
           tc::tmem_ld_32x32b_x32(tb + c0, v);
           tc::tmem_ld_wait();
           const int n = t.n0 + c0;
-          if (row_ok && n < p.N) epilogue_chunk(p, row, n, rs, v, bs + c0);
+          if (row_ok && n < p.N) epilogue_chunk<MODE>(p, row, n, rs, v, bs + c0);
         }
       }
       if (p.rowsum != nullptr && t.n0 == 0 && par == 0 && C::RS_COL + 32 <= C::TMEM_COLS) {
@@ -467,13 +484,32 @@ int make_tmap_2d(CUtensorMap* map, const void* base, long long dim0, long long d
   return 0;
 }
 
-template <int BN, int EW>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs a, int splits, cudaStream_t stream) {
+template <int BN, int EW, int MODE>
+int launch_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, int grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    VSN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+    VSN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
     attr_set = true;
   }
+  gemm_tc_kernel<BN, EW, MODE><<<grid, 64 + EW * 32, Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, a);
+  VSN_LAUNCH_CHECK();
+  return 0;
+}
+
+// which compile-time epilogue fits this call (0 = the generic one)
+int epilogue_mode(const GemmArgs& a, int bn) {
+  static int off = -1;     // VSN_GEMM_GENERIC=1: always the generic epilogue (measurements only)
+  if (off < 0) { const char* e = getenv("VSN_GEMM_GENERIC"); off = (e != nullptr && e[0] == '1') ? 1 : 0; }
+  if (off || !a.wide || a.N % bn != 0 || a.rowsum != nullptr || a.out_kind == 2) return 0;
+  if (a.act == 1 && a.out_kind == 0 && a.bias != nullptr && a.resid == nullptr) return 1;
+  if (a.act == 2 && a.out_kind == 0 && a.bias == nullptr && a.resid == nullptr) return 2;
+  if (a.act == 0 && a.out_kind == 1 && a.bias != nullptr && a.resid != nullptr) return 3;
+  if (a.act == 0 && a.out_kind == 0 && a.resid == nullptr) return 4;
+  return 0;
+}
+
+template <int BN, int EW>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs a, int splits, cudaStream_t stream) {
   a.splits = splits;
   const int tiles_m = ceil_div(a.M, BM), cols = ceil_div(a.N, BN) * splits;
   a.total_tiles = tiles_m * cols;
@@ -486,9 +522,16 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs a, int split
     grid = rows * cols;
     a.stationary = 1;
   }
-  gemm_tc_kernel<BN, EW><<<grid, 64 + EW * 32, Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, a);
-  VSN_LAUNCH_CHECK();
-  return 0;
+  if constexpr (EW == 16) {
+    switch (epilogue_mode(a, BN)) {
+      case 1: return launch_mode<BN, EW, 1>(tmA, tmB, a, grid, stream);
+      case 2: return launch_mode<BN, EW, 2>(tmA, tmB, a, grid, stream);
+      case 3: return launch_mode<BN, EW, 3>(tmA, tmB, a, grid, stream);
+      case 4: return launch_mode<BN, EW, 4>(tmA, tmB, a, grid, stream);
+      default: break;
+    }
+  }
+  return launch_mode<BN, EW, 0>(tmA, tmB, a, grid, stream);
 }
 
 // VSN_GEMM_EW=8|16 overrides the epilogue-warp heuristic (measurements only)
