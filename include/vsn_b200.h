@@ -36,7 +36,7 @@ long long vsn_launch_count(void);
  *   bias [N] fp32 (nullable); act: 0 none, 1 GELU(erf) with the bf16 pre-activation written to aux,
  *   2 multiply by GELU'(aux); resid fp32 [M, ldr] (nullable): out = resid + rowscale * (acc + bias);
  *   row_scale fp32 [M / rows_per_group] (nullable): per-sample DropPath factor; out_kind: 0 bf16 store,
- *   1 fp32 store, 2 fp32 atomic accumulate (required when split_k > 1).
+ *   1 fp32 store, 2 fp32 atomic accumulate (required when split_k > 1; split_k = 0 lets the library choose the split).
  *   rowsum_out fp32 [M] (nullable): += sum_k A(m,k), computed on the tensor cores against an all-ones tile --
  *   in a wgrad GEMM (A = dY read transposed) this is the bias gradient of the Linear, so no separate column
  *   reduction of dY is needed.

@@ -82,10 +82,7 @@ def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, dbias: Opt
     M, N = dy.shape
     K = x.shape[1]
     assert dy.dtype == BF16 and x.dtype == BF16 and dw.dtype == F32 and dw.is_contiguous()
-    tiles = math.ceil(N / 128) * math.ceil(K / (64 if K <= 64 else 128))
-    nkb = math.ceil(M / 64)
-    split = max(1, min(nkb, (2 * _N_SMS) // max(tiles, 1)))
-    gemm(dy, dy.stride(0), 1, x, x.stride(0), 1, N, K, M, dw, K, 2, split_k=split, rowsum=dbias)
+    gemm(dy, dy.stride(0), 1, x, x.stride(0), 1, N, K, M, dw, K, 2, split_k=0, rowsum=dbias)   # 0: the library picks
 
 
 # ------------------------------------------------------------------ LayerNorm
