@@ -222,6 +222,19 @@ class SwinTransformer3DBackbone(nn.Module):
         wi += 1
         real = tuple(-(-s // p) for s, p in zip(x.shape[2:], pe.patch_size))
         forced = DropPath.forced_masks
+        # DropPath factors of the whole forward pass in two launches (one Bernoulli draw over [2 * blocks, B] with the
+        # per-block keep probabilities, one division) instead of two tiny kernels per residual branch
+        dp_rows = None
+        if self.training and forced is None:
+            probs = [blk.drop_path.drop_prob if isinstance(blk.drop_path, DropPath) else 0.0
+                     for layer in self.layers for blk in layer.blocks]
+            if any(q > 0.0 for q in probs):
+                key = (t.device, tuple(probs))
+                if getattr(self, "_dp_keep_key", None) != key:
+                    keep = torch.tensor([1.0 - q for q in probs for _ in range(2)], device=t.device, dtype=torch.float32)
+                    self._dp_keep, self._dp_keep_key = keep[:, None], key
+                dp_rows = torch.bernoulli(self._dp_keep.expand(-1, B)) / self._dp_keep
+        bi = 0
         for layer in self.layers:
             C = t.shape[1]
             pdims = swin.padded_dims(real, layer.window_size)
@@ -233,11 +246,16 @@ class SwinTransformer3DBackbone(nn.Module):
                 shifted = any(s > 0 for s in blk.shift_size)
                 geom = ops.WindowGeom(B, pdims, blk.window_size, blk.shift_size if shifted else (0, 0, 0), shifted)
                 p = blk.drop_path.drop_prob if isinstance(blk.drop_path, DropPath) else 0.0
+                if dp_rows is not None:
+                    s1, s2 = (dp_rows[2 * bi], dp_rows[2 * bi + 1]) if p > 0.0 else (None, None)
+                else:
+                    s1 = swin.droppath_scale(p, B, t.device, self.training, forced)
+                    s2 = swin.droppath_scale(p, B, t.device, self.training, forced)
+                bi += 1
                 cfg = swin.BlockCfg(heads=blk.num_heads, hd=C // blk.num_heads, geom=geom, tokens_per_sample=tps,
                                     acc_key=id(blk),
                                     w16=tuple(self._shadow.view(wi + j) for j in range(4)),
-                                    scale1=swin.droppath_scale(p, B, t.device, self.training, forced),
-                                    scale2=swin.droppath_scale(p, B, t.device, self.training, forced))
+                                    scale1=s1, scale2=s2)
                 if prev_cfg is not None:
                     # backward hand-over of the bf16 input gradient from this block to the previous one
                     cfg.emit_for_prev, cfg.prev_scale2 = True, prev_cfg.scale2
