@@ -27,6 +27,7 @@ struct GemmArgs {
   int splits;           // K splits per output tile (fp32 atomic accumulation when > 1)
   int total_tiles;      // tiles_m * tiles_n * splits
   int stationary;       // 1: CTA b keeps column (n-tile, split) = b % cols for all its m-tiles (cols divides the grid)
+  int m_units;          // row units of the schedule: m-tiles, or pairs of m-tiles for CTA pairs
   void* out;
   long long ldo;
   int out_kind;         // 0 bf16 store, 1 fp32 store, 2 fp32 atomic add
@@ -45,25 +46,28 @@ struct GemmArgs {
   float* rowsum;        // [M] fp32 or null: rowsum[m] += sum_k A(m,k) (bias gradient of a Linear in its wgrad GEMM)
 };
 
-template <int BN>
+// TWO = CTA pair: a CTA holds its 128 rows of A and half of the B tile, so the same smem buys a deeper ring
+template <int BN, bool TWO = false>
 struct Cfg {
-  static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int B_BYTES = BN * BK * 2;                       // whole B tile
+  static constexpr int B_CTA_BYTES = TWO ? B_BYTES / 2 : B_BYTES;    // what one CTA stores
+  static constexpr int STAGE_BYTES = A_BYTES + B_CTA_BYTES;
   static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
   static constexpr int RS_COL = 2 * BN;              // two 16-column row-sum accumulators after the two tiles
   static constexpr int TMEM_COLS = 2 * BN + 32 <= 128 ? 128 : 2 * BN + 32 <= 256 ? 256 : 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias*/ +
                                     2048 /*ones tile*/;
+  static_assert(STAGE_BYTES % 1024 == 0, "stage bases must keep the 1024-byte alignment of the 128B swizzle");
 };
 
 
 struct TileCoord { int m0, n0, kb0, nkb; };
 
-__device__ __forceinline__ TileCoord decode_tile(const GemmArgs& p, int tile, int tiles_n, int bn) {
+__device__ __forceinline__ TileCoord decode_tile(const GemmArgs& p, int tile, int tiles_n, int bn, int mul, int rank) {
   const int split = tile % p.splits, mn = tile / p.splits;
   TileCoord t;
   t.n0 = (mn % tiles_n) * bn;
-  t.m0 = (mn / tiles_n) * BM;
+  t.m0 = ((mn / tiles_n) * mul + rank) * BM;
   const int nkb_total = (p.K + BK - 1) / BK;
   t.kb0 = split * p.kb_per_split;
   t.nkb = min(nkb_total, t.kb0 + p.kb_per_split) - t.kb0;
@@ -72,21 +76,27 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmArgs& p, int tile, in
 // k-th tile of this CTA, or false when it has none left.  Stationary schedule: the CTA keeps its
 // (n-tile, split) column and walks the m-tiles with stride gridDim.x / columns, so the weight tile and the
 // bias slice stay the same for the whole kernel; otherwise tiles are dealt round-robin.
-__device__ __forceinline__ bool cta_tile(const GemmArgs& p, int k, int tiles_n, int bn, TileCoord& t) {
+// TWO (CTA pair, cta_group::2): the schedule runs over 256-row units, rows [0,128) of a unit belong to the leader
+// CTA (rank 0), rows [128,256) to its peer; the lower half of the last unit may lie below the matrix (TMA fills
+// zeros, the epilogue skips the rows).
+template <bool TWO>
+__device__ __forceinline__ bool cta_tile(const GemmArgs& p, int k, int tiles_n, int bn, int rank, TileCoord& t) {
+  const int vb = TWO ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int vg = TWO ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  constexpr int MUL = TWO ? 2 : 1;
   if (p.stationary) {
     const int cols = tiles_n * p.splits;
-    const int col = blockIdx.x % cols, m_tile = blockIdx.x / cols + k * (gridDim.x / cols);
-    if (m_tile * BM >= p.M) return false;
-    t = decode_tile(p, m_tile * cols + col, tiles_n, bn);
+    const int col = vb % cols, m_unit = vb / cols + k * (vg / cols);
+    if (m_unit >= p.m_units) return false;
+    t = decode_tile(p, m_unit * cols + col, tiles_n, bn, MUL, rank);
     return true;
   }
-  const int tile = blockIdx.x + k * gridDim.x;
+  const int tile = vb + k * vg;
   if (tile >= p.total_tiles) return false;
-  t = decode_tile(p, tile, tiles_n, bn);
+  t = decode_tile(p, tile, tiles_n, bn, MUL, rank);
   return true;
 }
 
-// One 32-column chunk of an output row: v = fp32 accumulators from TMEM, bias_s = the chunk's bias in smem.
 // MODE specialises the hot epilogues at compile time (straight-line code, no per-chunk parameter loads and uniform
 // branches); MODE 0 reads everything from the arguments:
 //   1 = bias + GELU, bf16 output + saved pre-activation, 256-bit stores, full tiles (the fc1 forward)
@@ -259,11 +269,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& pa, int row, int 
 // EW = number of epilogue warps (8 or 16).  Small-K problems are bound by the epilogue (one MUFU + ~25 FP32
 // instructions per element for the GELU variants, the stores for the others), so they run 16 epilogue warps
 // (4 per scheduler) to hide latency; large-K problems keep 8 with software-pipelined TMEM loads.
-template <int BN, int EW, int MODE>
+template <int BN, int EW, int MODE, bool TWO>
 __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                   const __grid_constant__ CUtensorMap tmB,
                                                                   const GemmArgs p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, TWO>;
   constexpr int EPI_THREADS = EW * 32;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -278,6 +288,11 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tiles_n = (p.N + BN - 1) / BN;
+  // TWO: a pair of CTAs (cluster of 2) works on 256 x BN tiles with cta_group::2 MMAs issued by the leader: every
+  // CTA streams its own 128 rows of A and only HALF of the B tile, which is what the deep-K problems of the late
+  // stages are bound by (L2 -> SM operand traffic).  full[] and acc_empty[] live in the leader, empty[] and
+  // acc_full[] are signalled in both CTAs by multicast commits.
+  const int rank = TWO ? static_cast<int>(tc::cluster_ctarank()) : 0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -286,19 +301,23 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
     }
     for (int b = 0; b < 2; ++b) {
       tc::mbar_init(&acc_full[b], 1);
-      tc::mbar_init(&acc_empty[b], EPI_THREADS);
+      tc::mbar_init(&acc_empty[b], TWO ? 2 * EPI_THREADS : EPI_THREADS);
     }
     tc::fence_barrier_init();
     tc::prefetch_tmap(&tmA);
     tc::prefetch_tmap(&tmB);
   }
-  if (warp == 1) tc::tmem_alloc(tmem_slot, C::TMEM_COLS);
+  if (warp == 1) {
+    if constexpr (TWO) tc::tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
+    else tc::tmem_alloc(tmem_slot, C::TMEM_COLS);
+  }
   if (p.rowsum != nullptr) {
     for (int i = threadIdx.x; i < 512; i += blockDim.x) reinterpret_cast<uint32_t*>(ones_s)[i] = 0x3F803F80u;   // bf16 1.0 pairs
     tc::fence_proxy_async();
   }
   tc::fence_before_sync();
   __syncthreads();
+  if constexpr (TWO) tc::cluster_sync();    // the peer's barriers are initialised before anything targets them
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -306,15 +325,33 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
     if (lane == 0) {
       int it = 0;   // k-blocks issued so far (ring position)
       TileCoord t;
-      for (int lt = 0; cta_tile(p, lt, tiles_n, BN, t); ++lt) {
+      for (int lt = 0; cta_tile<TWO>(p, lt, tiles_n, BN, rank, t); ++lt) {
         for (int i = 0; i < t.nkb; ++i, ++it) {
           const int s = it % C::STAGES;
           const uint32_t ph = (it / C::STAGES) & 1;
           tc::mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * C::STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          tc::mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
           const int k0 = (t.kb0 + i) * BK;
+          if constexpr (TWO) {
+            // both CTAs' bytes (2 x A + the two halves of B) land on the leader's barrier
+            if (rank == 0) tc::mbar_arrive_expect_tx(&full_bar[s], 2 * A_BYTES + C::B_BYTES);
+            if (!p.a_mn) {
+              tc::tma_load_2d_pair(sa, &tmA, &full_bar[s], k0, t.m0);
+            } else {
+              tc::tma_load_2d_pair(sa, &tmA, &full_bar[s], t.m0, k0);
+              tc::tma_load_2d_pair(sa + 8192, &tmA, &full_bar[s], t.m0 + 64, k0);
+            }
+            if (!p.b_mn) {
+              tc::tma_load_2d_pair(sb, &tmB, &full_bar[s], k0, t.n0 + rank * (BN / 2));     // box {64 k, BN/2 rows}
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 128; ++j)
+                tc::tma_load_2d_pair(sb + j * 8192, &tmB, &full_bar[s], t.n0 + rank * (BN / 2) + j * 64, k0);
+            }
+            continue;
+          }
+          tc::mbar_arrive_expect_tx(&full_bar[s], A_BYTES + C::B_BYTES);
           if (!p.a_mn) {
             tc::tma_load_2d(sa, &tmA, &full_bar[s], k0, t.m0);           // box {64 k, 128 rows}
           } else {
@@ -332,8 +369,9 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // MMA issuer: the warp runs converged (all lanes wait on the barriers), one elected lane issues
-    {
-      const uint32_t idesc = tc::make_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+    // (CTA pairs: the leader's warp issues for both CTAs, the peer's warp only owns its TMEM allocation)
+    if (!TWO || rank == 0) {
+      const uint32_t idesc = tc::make_idesc_bf16(TWO ? 2 * BM : BM, BN, p.a_mn, p.b_mn);
       const uint32_t idesc_rs = tc::make_idesc_bf16(BM, 16, p.a_mn, 0);
       const uint64_t ones_desc = tc::make_smem_desc_sw128(tc::smem_u32(ones_s), 16, 1024);
       const uint32_t a_step = p.a_mn ? 2048u : 32u;   // bytes per K=16 step
@@ -342,7 +380,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
       const uint64_t bdesc0 = tc::make_smem_desc_sw128(tc::smem_u32(smem) + A_BYTES, p.b_mn ? 8192u : 16u, 1024);
       int it = 0;
       TileCoord t;
-      for (int lt = 0; cta_tile(p, lt, tiles_n, BN, t); ++lt) {
+      for (int lt = 0; cta_tile<TWO>(p, lt, tiles_n, BN, rank, t); ++lt) {
         const int buf = lt & 1;
         tc::mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);
         tc::fence_after_sync();
@@ -357,6 +395,17 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
           const uint64_t bd = tc::desc_advance(bdesc0, s * C::STAGE_BYTES);
           const int krem = p.K - (t.kb0 + i) * BK;
           const int ksteps = krem >= BK ? BK / 16 : (krem + 15) / 16;
+          if constexpr (TWO) {
+            if (tc::elect_one()) {
+              for (int k = 0; k < ksteps; ++k)
+                tc::mma_bf16_ss_pair(d, tc::desc_advance(ad, k * a_step), tc::desc_advance(bd, k * b_step), idesc,
+                                     (i > 0 || k > 0) ? 1u : 0u);
+              tc::mma_commit_pair(&empty_bar[s], 3);                       // the stage is free in both CTAs
+              if (i == t.nkb - 1) tc::mma_commit_pair(&acc_full[buf], 3);  // both halves of the accumulator
+            }
+            __syncwarp();
+            continue;
+          }
           if (tc::elect_one()) {
             if (ksteps == BK / 16) {
 #pragma unroll
@@ -390,7 +439,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
     const int et = threadIdx.x - 64;
     constexpr int NCH = (BN / 32 + NPAR - 1) / NPAR;   // chunks per warp (upper bound)
     TileCoord t;
-    for (int lt = 0; cta_tile(p, lt, tiles_n, BN, t); ++lt) {
+    for (int lt = 0; cta_tile<TWO>(p, lt, tiles_n, BN, rank, t); ++lt) {
       const int buf = lt & 1;
       const int row = t.m0 + lg * 32 + lane;
       // The tile's bias slice goes through smem (broadcast reads instead of dependent global loads per chunk).
@@ -438,14 +487,17 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
         if (row_ok) atomicAdd(p.rowsum + row, __uint_as_float(rsv));
       }
       tc::fence_before_sync();
-      tc::mbar_arrive(&acc_empty[buf]);
+      if constexpr (TWO) tc::mbar_arrive_cluster(tc::leader_addr(&acc_empty[buf]));
+      else tc::mbar_arrive(&acc_empty[buf]);
     }
   }
   tc::fence_before_sync();
   __syncthreads();
+  if constexpr (TWO) tc::cluster_sync();    // no CTA leaves while its peer may still signal its barriers / read its smem
   if (warp == 1) {
     tc::fence_after_sync();
-    tc::tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if constexpr (TWO) tc::tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+    else tc::tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -484,14 +536,29 @@ int make_tmap_2d(CUtensorMap* map, const void* base, long long dim0, long long d
   return 0;
 }
 
-template <int BN, int EW, int MODE>
+template <int BN, int EW, int MODE, bool TWO>
 int launch_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, int grid, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    VSN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+    VSN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EW, MODE, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg<BN, TWO>::SMEM_BYTES));
     attr_set = true;
   }
-  gemm_tc_kernel<BN, EW, MODE><<<grid, 64 + EW * 32, Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, a);
+  if constexpr (TWO) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * grid);
+    cfg.blockDim = dim3(64 + EW * 32);
+    cfg.dynamicSmemBytes = Cfg<BN, true>::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VSN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EW, MODE, true>, tmA, tmB, a));
+  } else {
+    gemm_tc_kernel<BN, EW, MODE, false><<<grid, 64 + EW * 32, Cfg<BN, false>::SMEM_BYTES, stream>>>(tmA, tmB, a);
+  }
   VSN_LAUNCH_CHECK();
   return 0;
 }
@@ -509,29 +576,42 @@ int epilogue_mode(const GemmArgs& a, int bn) {
 }
 
 template <int BN, int EW>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs a, int splits, cudaStream_t stream) {
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs a, int splits, bool pair, cudaStream_t stream) {
   a.splits = splits;
   const int tiles_m = ceil_div(a.M, BM), cols = ceil_div(a.N, BN) * splits;
-  a.total_tiles = tiles_m * cols;
-  int grid = a.total_tiles < vsn_num_sms() ? a.total_tiles : vsn_num_sms();
+  const int mul = pair ? 2 : 1;
+  a.m_units = ceil_div(tiles_m, mul);
+  a.total_tiles = a.m_units * cols;
+  const int slots = vsn_num_sms() / mul;               // CTAs (or CTA pairs) the chip runs at once
+  int grid = a.total_tiles < slots ? a.total_tiles : slots;
   a.stationary = 0;
   // (measured: pays for few wide column tiles; round-robin is better for split-K and for many / narrow columns)
-  if (splits == 1 && (cols == 1 || (BN >= 128 && cols <= 4)) && tiles_m >= 2 * (vsn_num_sms() / cols)) {
+  if (splits == 1 && (cols == 1 || (BN >= 128 && cols <= 4)) && a.m_units >= 2 * (slots / cols)) {
     // n-stationary persistent schedule: as many rows of `cols` CTAs as fit on the chip
-    const int rows = vsn_num_sms() / cols < tiles_m ? vsn_num_sms() / cols : tiles_m;
+    const int rows = slots / cols < a.m_units ? slots / cols : a.m_units;
     grid = rows * cols;
     a.stationary = 1;
   }
   if constexpr (EW == 16) {
-    switch (epilogue_mode(a, BN)) {
-      case 1: return launch_mode<BN, EW, 1>(tmA, tmB, a, grid, stream);
-      case 2: return launch_mode<BN, EW, 2>(tmA, tmB, a, grid, stream);
-      case 3: return launch_mode<BN, EW, 3>(tmA, tmB, a, grid, stream);
-      case 4: return launch_mode<BN, EW, 4>(tmA, tmB, a, grid, stream);
+    const int mode = epilogue_mode(a, BN);
+    if (pair) {
+      switch (mode) {
+        case 1: return launch_mode<BN, EW, 1, true>(tmA, tmB, a, grid, stream);
+        case 2: return launch_mode<BN, EW, 2, true>(tmA, tmB, a, grid, stream);
+        case 3: return launch_mode<BN, EW, 3, true>(tmA, tmB, a, grid, stream);
+        case 4: return launch_mode<BN, EW, 4, true>(tmA, tmB, a, grid, stream);
+        default: return launch_mode<BN, EW, 0, true>(tmA, tmB, a, grid, stream);
+      }
+    }
+    switch (mode) {
+      case 1: return launch_mode<BN, EW, 1, false>(tmA, tmB, a, grid, stream);
+      case 2: return launch_mode<BN, EW, 2, false>(tmA, tmB, a, grid, stream);
+      case 3: return launch_mode<BN, EW, 3, false>(tmA, tmB, a, grid, stream);
+      case 4: return launch_mode<BN, EW, 4, false>(tmA, tmB, a, grid, stream);
       default: break;
     }
   }
-  return launch_mode<BN, EW, 0>(tmA, tmB, a, grid, stream);
+  return launch_mode<BN, EW, 0, false>(tmA, tmB, a, grid, stream);
 }
 
 // VSN_GEMM_EW=8|16 overrides the epilogue-warp heuristic (measurements only)
@@ -598,12 +678,23 @@ extern "C" int vsn_gemm_bf16(const void* A, long long lda, int a_mn, const void*
       BN = next;
     }
   }
+  // CTA pairs (cta_group::2, 256 x BN tiles): for store epilogues with at least two m-tiles; an MN-major B operand is
+  // loaded in 64-column boxes, so its half tile must be a whole number of them.
+  bool pair;
+  {
+    static int mode = -1;   // VSN_GEMM_PAIR=0|1 forces CTA pairs off / on wherever they are possible (measurements)
+    if (mode < 0) { const char* e = getenv("VSN_GEMM_PAIR"); mode = e ? atoi(e) : 2; }
+    const bool ew16 = out_kind != 2 && forced_ew() != 8;     // the pair kernels are built with 16 epilogue warps
+    const bool possible = ew16 && rowsum_out == nullptr && ceil_div(M, BM) >= 2 && (!b_mn || BN % 128 == 0);
+    // (measured: pays when the problem is not streaming one operand from HBM, i.e. both N and K reasonably large)
+    pair = possible && (mode == 1 || (mode == 2 && N >= 192 && K >= 192));
+  }
   CUtensorMap tmA, tmB;
   int rc;
   if (!a_mn) rc = make_tmap_2d(&tmA, A, K, M, lda, BK, BM);
   else rc = make_tmap_2d(&tmA, A, M, K, lda, 64, BK);
   if (rc) return rc;
-  if (!b_mn) rc = make_tmap_2d(&tmB, B, K, N, ldb, BK, BN);
+  if (!b_mn) rc = make_tmap_2d(&tmB, B, K, N, ldb, BK, pair ? BN / 2 : BN);
   else rc = make_tmap_2d(&tmB, B, N, K, ldb, 64, BK);
   if (rc) return rc;
 
@@ -636,18 +727,18 @@ extern "C" int vsn_gemm_bf16(const void* A, long long lda, int a_mn, const void*
   if (forced_ew() == 8 || forced_ew() == 16) ew = forced_ew();
   if (ew == 16) {
     switch (BN) {
-      case 64: return launch<64, 16>(tmA, tmB, a, splits, s);
-      case 96: return launch<96, 16>(tmA, tmB, a, splits, s);
-      case 192: return launch<192, 16>(tmA, tmB, a, splits, s);
-      case 256: return launch<256, 16>(tmA, tmB, a, splits, s);
-      default: return launch<128, 16>(tmA, tmB, a, splits, s);
+      case 64: return launch<64, 16>(tmA, tmB, a, splits, pair, s);
+      case 96: return launch<96, 16>(tmA, tmB, a, splits, pair, s);
+      case 192: return launch<192, 16>(tmA, tmB, a, splits, pair, s);
+      case 256: return launch<256, 16>(tmA, tmB, a, splits, pair, s);
+      default: return launch<128, 16>(tmA, tmB, a, splits, pair, s);
     }
   }
   switch (BN) {
-    case 64: return launch<64, 8>(tmA, tmB, a, splits, s);
-    case 96: return launch<96, 8>(tmA, tmB, a, splits, s);
-    case 192: return launch<192, 8>(tmA, tmB, a, splits, s);
-    case 256: return launch<256, 8>(tmA, tmB, a, splits, s);
-    default: return launch<128, 8>(tmA, tmB, a, splits, s);
+    case 64: return launch<64, 8>(tmA, tmB, a, splits, pair, s);
+    case 96: return launch<96, 8>(tmA, tmB, a, splits, pair, s);
+    case 192: return launch<192, 8>(tmA, tmB, a, splits, pair, s);
+    case 256: return launch<256, 8>(tmA, tmB, a, splits, pair, s);
+    default: return launch<128, 8>(tmA, tmB, a, splits, pair, s);
   }
 }

@@ -44,6 +44,8 @@ class WeightShadow:
     def refresh(self) -> None:
         from .optim import MultiTensorTable
         key = tuple((p.data_ptr(), p.numel()) for p in self.params)
+        if key == self._key and GradAccumulation.active and not GradAccumulation.first:
+            return      # a later micro-batch of the same optimiser step: the masters have not been written since
         if key != self._key:
             dev = self.params[0].device
             sizes = [(p.numel() + 7) // 8 * 8 for p in self.params]   # keep every view 16-byte aligned
@@ -75,15 +77,16 @@ class GradAccumulation:
 
     active = False
     final = True
+    first = True        # first micro-batch of the optimiser step (later ones see unchanged weights)
     store: dict = {}
 
     @classmethod
-    def begin(cls, final: bool) -> None:
-        cls.active, cls.final = True, final
+    def begin(cls, final: bool, first: bool = True) -> None:
+        cls.active, cls.final, cls.first = True, final, first
 
     @classmethod
     def end(cls) -> None:
-        cls.active, cls.final = False, True
+        cls.active, cls.final, cls.first = False, True, True
         if not cls.store:
             return
         left = len(cls.store)

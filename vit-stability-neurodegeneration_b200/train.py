@@ -55,7 +55,7 @@ class TrainStep:
         from .swin import GradAccumulation
         for i, (x, y) in enumerate(batches):
             last = i == n - 1
-            GradAccumulation.begin(final=last)           # block gradients are summed in-kernel over the micro-batches
+            GradAccumulation.begin(final=last, first=i == 0)   # block gradients are summed in-kernel over the micro-batches
             if self.grad_sync is not None:
                 ctx = nullcontext() if last else self.grad_sync.no_sync()
             else:
