@@ -63,39 +63,57 @@ struct Cfg {
 
 struct TileCoord { int m0, n0, kb0, nkb; };
 
-__device__ __forceinline__ TileCoord decode_tile(const GemmArgs& p, int tile, int tiles_n, int bn, int mul, int rank) {
-  const int split = tile % p.splits, mn = tile / p.splits;
-  TileCoord t;
-  t.n0 = (mn % tiles_n) * bn;
-  t.m0 = ((mn / tiles_n) * mul + rank) * BM;
-  const int nkb_total = (p.K + BK - 1) / BK;
-  t.kb0 = split * p.kb_per_split;
-  t.nkb = min(nkb_total, t.kb0 + p.kb_per_split) - t.kb0;
-  return t;
-}
-// k-th tile of this CTA, or false when it has none left.  Stationary schedule: the CTA keeps its
-// (n-tile, split) column and walks the m-tiles with stride gridDim.x / columns, so the weight tile and the
-// bias slice stay the same for the whole kernel; otherwise tiles are dealt round-robin.
+// Walks the tiles of this CTA.  Stationary schedule: the CTA keeps its (n-tile, split) column and walks the row
+// units with stride grid / columns, so the weight tile and the bias slice stay the same for the whole kernel;
+// otherwise tiles (split fastest, then n, then rows) are dealt round-robin over the grid.
 // TWO (CTA pair, cta_group::2): the schedule runs over 256-row units, rows [0,128) of a unit belong to the leader
 // CTA (rank 0), rows [128,256) to its peer; the lower half of the last unit may lie below the matrix (TMA fills
 // zeros, the epilogue skips the rows).
+// All integer divisions happen once, in the constructor: the small-K problems of the early stages run tens of tiles
+// per CTA with little work each, and the per-tile div/mod chains were 40 % of their executed instructions.
 template <bool TWO>
-__device__ __forceinline__ bool cta_tile(const GemmArgs& p, int k, int tiles_n, int bn, int rank, TileCoord& t) {
-  const int vb = TWO ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int vg = TWO ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-  constexpr int MUL = TWO ? 2 : 1;
-  if (p.stationary) {
-    const int cols = tiles_n * p.splits;
-    const int col = vb % cols, m_unit = vb / cols + k * (vg / cols);
-    if (m_unit >= p.m_units) return false;
-    t = decode_tile(p, m_unit * cols + col, tiles_n, bn, MUL, rank);
+struct TileIter {
+  int m, n, split;          // current row unit, n-tile, split
+  int dm, dn, ds;           // grid stride decomposed over (rows, n-tiles, splits)
+  int tiles_n, splits, m_units, bn, rank, kbps, nkb_total;
+  bool first;
+  __device__ __forceinline__ TileIter(const GemmArgs& p, int tiles_n_, int bn_, int rank_) {
+    const int vb = TWO ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int vg = TWO ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    tiles_n = tiles_n_; splits = p.splits; m_units = p.m_units; bn = bn_; rank = rank_;
+    kbps = p.kb_per_split; nkb_total = (p.K + BK - 1) / BK;
+    const int cols = tiles_n * splits;
+    int start, stride;
+    if (p.stationary) {              // the CTA's column never changes: only the row unit advances
+      start = (vb / cols) * cols + vb % cols;
+      stride = (vg / cols) * cols;
+    } else {
+      start = vb;
+      stride = vg;
+    }
+    split = start % splits; n = (start / splits) % tiles_n; m = start / cols;
+    ds = stride % splits; dn = (stride / splits) % tiles_n; dm = stride / cols;
+    first = true;
+  }
+  __device__ __forceinline__ bool next(TileCoord& t) {
+    if (!first) {
+      split += ds;
+      int c = split >= splits ? 1 : 0;
+      split -= c * splits;
+      n += dn + c;
+      c = n >= tiles_n ? 1 : 0;
+      n -= c * tiles_n;
+      m += dm + c;
+    }
+    first = false;
+    if (m >= m_units) return false;
+    t.n0 = n * bn;
+    t.m0 = (m * (TWO ? 2 : 1) + rank) * BM;
+    t.kb0 = split * kbps;
+    t.nkb = min(nkb_total, t.kb0 + kbps) - t.kb0;
     return true;
   }
-  const int tile = vb + k * vg;
-  if (tile >= p.total_tiles) return false;
-  t = decode_tile(p, tile, tiles_n, bn, MUL, rank);
-  return true;
-}
+};
 
 // MODE specialises the hot epilogues at compile time (straight-line code, no per-chunk parameter loads and uniform
 // branches); MODE 0 reads everything from the arguments:
@@ -323,12 +341,12 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
 
   if (warp == 0) {
     if (lane == 0) {
-      int it = 0;   // k-blocks issued so far (ring position)
+      int s = 0;          // ring position
+      uint32_t ph = 0;    // and its phase
       TileCoord t;
-      for (int lt = 0; cta_tile<TWO>(p, lt, tiles_n, BN, rank, t); ++lt) {
-        for (int i = 0; i < t.nkb; ++i, ++it) {
-          const int s = it % C::STAGES;
-          const uint32_t ph = (it / C::STAGES) & 1;
+      TileIter<TWO> tiles(p, tiles_n, BN, rank);
+      while (tiles.next(t)) {
+        for (int i = 0; i < t.nkb; ++i, s = (s + 1 == C::STAGES ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
           tc::mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * C::STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
@@ -378,17 +396,17 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
       const uint32_t b_step = p.b_mn ? 2048u : 32u;
       const uint64_t adesc0 = tc::make_smem_desc_sw128(tc::smem_u32(smem), p.a_mn ? 8192u : 16u, 1024);
       const uint64_t bdesc0 = tc::make_smem_desc_sw128(tc::smem_u32(smem) + A_BYTES, p.b_mn ? 8192u : 16u, 1024);
-      int it = 0;
+      int s = 0;
+      uint32_t ph = 0;
       TileCoord t;
-      for (int lt = 0; cta_tile<TWO>(p, lt, tiles_n, BN, rank, t); ++lt) {
+      TileIter<TWO> tiles(p, tiles_n, BN, rank);
+      for (int lt = 0; tiles.next(t); ++lt) {
         const int buf = lt & 1;
         tc::mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);
         tc::fence_after_sync();
         const uint32_t d = tmem_base + buf * BN;
         const bool do_rs = p.rowsum != nullptr && t.n0 == 0 && C::RS_COL + 32 <= C::TMEM_COLS;
-        for (int i = 0; i < t.nkb; ++i, ++it) {
-          const int s = it % C::STAGES;
-          const uint32_t ph = (it / C::STAGES) & 1;
+        for (int i = 0; i < t.nkb; ++i, s = (s + 1 == C::STAGES ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
           tc::mbar_wait(&full_bar[s], ph);
           tc::fence_after_sync();
           const uint64_t ad = tc::desc_advance(adesc0, s * C::STAGE_BYTES);
@@ -439,7 +457,8 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
     const int et = threadIdx.x - 64;
     constexpr int NCH = (BN / 32 + NPAR - 1) / NPAR;   // chunks per warp (upper bound)
     TileCoord t;
-    for (int lt = 0; cta_tile<TWO>(p, lt, tiles_n, BN, rank, t); ++lt) {
+    TileIter<TWO> tiles(p, tiles_n, BN, rank);
+    for (int lt = 0; tiles.next(t); ++lt) {
       const int buf = lt & 1;
       const int row = t.m0 + lg * 32 + lane;
       // The tile's bias slice goes through smem (broadcast reads instead of dependent global loads per chunk).
@@ -586,7 +605,9 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs a, int split
   int grid = a.total_tiles < slots ? a.total_tiles : slots;
   a.stationary = 0;
   // (measured: pays for few wide column tiles; round-robin is better for split-K and for many / narrow columns)
-  if (splits == 1 && (cols == 1 || (BN >= 128 && cols <= 4)) && a.m_units >= 2 * (slots / cols)) {
+  static int stat_min_bn = -1;   // VSN_GEMM_STAT_BN: smallest tile width that takes the n-stationary schedule (measurements)
+  if (stat_min_bn < 0) { const char* e = getenv("VSN_GEMM_STAT_BN"); stat_min_bn = e ? atoi(e) : 96; }
+  if (splits == 1 && (cols == 1 || (BN >= stat_min_bn && cols <= 4)) && a.m_units >= 2 * (slots / cols)) {
     // n-stationary persistent schedule: as many rows of `cols` CTAs as fit on the chip
     const int rows = slots / cols < a.m_units ? slots / cols : a.m_units;
     grid = rows * cols;
