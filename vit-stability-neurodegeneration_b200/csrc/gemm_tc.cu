@@ -345,8 +345,14 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
       uint32_t ph = 0;    // and its phase
       TileCoord t;
       TileIter<TWO> tiles(p, tiles_n, BN, rank);
+      // B stays resident: with the n-stationary schedule and a k-extent that divides the ring, stage s always holds
+      // the same k-block of the same weight tile, so it is fetched on the first pass over the ring only (the weight
+      // tile re-read per output tile was a third of the L2 -> SM traffic of the K = 96 problems)
+      const int nkb_tile = min((p.K + BK - 1) / BK, p.kb_per_split);
+      const bool b_resident = !TWO && p.stationary && p.splits == 1 && C::STAGES % nkb_tile == 0;
+      int issued = 0;
       while (tiles.next(t)) {
-        for (int i = 0; i < t.nkb; ++i, s = (s + 1 == C::STAGES ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
+        for (int i = 0; i < t.nkb; ++i, ++issued, s = (s + 1 == C::STAGES ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
           tc::mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * C::STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
@@ -369,14 +375,16 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
             }
             continue;
           }
-          tc::mbar_arrive_expect_tx(&full_bar[s], A_BYTES + C::B_BYTES);
+          const bool load_b = !b_resident || issued < C::STAGES;
+          tc::mbar_arrive_expect_tx(&full_bar[s], load_b ? A_BYTES + C::B_BYTES : A_BYTES);
           if (!p.a_mn) {
             tc::tma_load_2d(sa, &tmA, &full_bar[s], k0, t.m0);           // box {64 k, 128 rows}
           } else {
             tc::tma_load_2d(sa, &tmA, &full_bar[s], t.m0, k0);           // box {64 m, 64 k-rows}
             tc::tma_load_2d(sa + 8192, &tmA, &full_bar[s], t.m0 + 64, k0);
           }
-          if (!p.b_mn) {
+          if (!load_b) {
+          } else if (!p.b_mn) {
             tc::tma_load_2d(sb, &tmB, &full_bar[s], k0, t.n0);           // box {64 k, BN rows}
           } else {
 #pragma unroll
