@@ -339,20 +339,23 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
+  // B stays resident: with the n-stationary schedule (the CTA's weight tile never changes) the ring is cut to a
+  // multiple of the tile's k-blocks, so stage s always holds the same k-block of the same weight tile and B is
+  // fetched on the first pass over the ring only (the weight tile re-read per output tile was a third of the
+  // L2 -> SM traffic of the K = 96 problems).
+  const int nkb_tile = min((p.K + BK - 1) / BK, p.kb_per_split);
+  const bool b_resident = !TWO && p.stationary && p.splits == 1 && nkb_tile <= C::STAGES;
+  const int ring = b_resident ? (C::STAGES / nkb_tile) * nkb_tile : C::STAGES;
+
   if (warp == 0) {
     if (lane == 0) {
       int s = 0;          // ring position
       uint32_t ph = 0;    // and its phase
       TileCoord t;
       TileIter<TWO> tiles(p, tiles_n, BN, rank);
-      // B stays resident: with the n-stationary schedule and a k-extent that divides the ring, stage s always holds
-      // the same k-block of the same weight tile, so it is fetched on the first pass over the ring only (the weight
-      // tile re-read per output tile was a third of the L2 -> SM traffic of the K = 96 problems)
-      const int nkb_tile = min((p.K + BK - 1) / BK, p.kb_per_split);
-      const bool b_resident = !TWO && p.stationary && p.splits == 1 && C::STAGES % nkb_tile == 0;
       int issued = 0;
       while (tiles.next(t)) {
-        for (int i = 0; i < t.nkb; ++i, ++issued, s = (s + 1 == C::STAGES ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
+        for (int i = 0; i < t.nkb; ++i, ++issued, s = (s + 1 == ring ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
           tc::mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * C::STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
@@ -375,7 +378,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
             }
             continue;
           }
-          const bool load_b = !b_resident || issued < C::STAGES;
+          const bool load_b = !b_resident || issued < ring;
           tc::mbar_arrive_expect_tx(&full_bar[s], load_b ? A_BYTES + C::B_BYTES : A_BYTES);
           if (!p.a_mn) {
             tc::tma_load_2d(sa, &tmA, &full_bar[s], k0, t.m0);           // box {64 k, 128 rows}
@@ -414,7 +417,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
         tc::fence_after_sync();
         const uint32_t d = tmem_base + buf * BN;
         const bool do_rs = p.rowsum != nullptr && t.n0 == 0 && C::RS_COL + 32 <= C::TMEM_COLS;
-        for (int i = 0; i < t.nkb; ++i, s = (s + 1 == C::STAGES ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
+        for (int i = 0; i < t.nkb; ++i, s = (s + 1 == ring ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
           tc::mbar_wait(&full_bar[s], ph);
           tc::fence_after_sync();
           const uint64_t ad = tc::desc_advance(adesc0, s * C::STAGE_BYTES);
