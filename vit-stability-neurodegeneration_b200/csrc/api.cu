@@ -1,5 +1,6 @@
 // C-ABI plumbing shared by every entry point: error string, version, device gate.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 
@@ -21,6 +22,13 @@ int vsn_num_sms() {
     if (sms <= 0) sms = 148;
   }
   return sms;
+}
+
+// Programmatic dependent launch for the kernels that support it (VSN_PDL=0 turns it off: measurements / debugging)
+bool vsn_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("VSN_PDL"); on = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  return on != 0;
 }
 
 // Number of kernel launches issued by this library since load (all threads); bench.py reports the

@@ -38,6 +38,7 @@ void vsn_count_launch();
   } while (0)
 
 int vsn_num_sms();
+bool vsn_pdl_enabled();
 
 // ---- small device utilities ----------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
@@ -181,6 +182,14 @@ __device__ __forceinline__ void ld_global_v8(const void* p, uint32_t* v) {
   asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
 }
+
+// ---- programmatic dependent launch (sm_90+) -------------------------------------------------------------------
+// pdl_trigger(): this grid no longer needs to finish before the next kernel of the stream may be SCHEDULED (its CTAs
+// take SM resources as ours retire and run their prologue); pdl_wait(): block until every kernel the stream ordered
+// before this one has completed and its memory is visible.  A kernel launched with the attribute must call
+// pdl_wait() before it touches global memory; one launched without it is unaffected by either call.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ __forceinline__ long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }

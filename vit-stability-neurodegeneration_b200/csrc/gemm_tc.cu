@@ -338,6 +338,10 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
   if constexpr (TWO) tc::cluster_sync();    // the peer's barriers are initialised before anything targets them
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // Everything above (barriers, TMEM, descriptor prefetch) ran while the previous kernel of the stream was still
+  // finishing; from here on its results are read.
+  pdl_trigger();
+  pdl_wait();
 
   // B stays resident: with the n-stationary schedule (the CTA's weight tile never changes) the ring is cut to a
   // multiple of the tile's k-blocks, so stage s always holds the same k-block of the same weight tile and B is
@@ -574,21 +578,26 @@ int launch_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& 
                                   Cfg<BN, TWO>::SMEM_BYTES));
     attr_set = true;
   }
-  if constexpr (TWO) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * grid);
-    cfg.blockDim = dim3(64 + EW * 32);
-    cfg.dynamicSmemBytes = Cfg<BN, true>::SMEM_BYTES;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    VSN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EW, MODE, true>, tmA, tmB, a));
-  } else {
-    gemm_tc_kernel<BN, EW, MODE, false><<<grid, 64 + EW * 32, Cfg<BN, false>::SMEM_BYTES, stream>>>(tmA, tmB, a);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((TWO ? 2 : 1) * grid);
+  cfg.blockDim = dim3(64 + EW * 32);
+  cfg.dynamicSmemBytes = Cfg<BN, TWO>::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (vsn_pdl_enabled()) {     // programmatic dependent launch: the prologue overlaps the previous kernel's tail
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
   }
+  if constexpr (TWO) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  VSN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EW, MODE, TWO>, tmA, tmB, a));
   VSN_LAUNCH_CHECK();
   return 0;
 }

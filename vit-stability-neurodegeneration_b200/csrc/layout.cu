@@ -74,6 +74,7 @@ __device__ __forceinline__ void load4<bf16>(const bf16* p, float* v) {
 template <typename InT>
 __global__ void __launch_bounds__(256) patch_gather444_kernel(const InT* __restrict__ vol, bf16* __restrict__ out, int B,
                                                               int D, int H, int W, int gd, int gh, int gw) {
+  pdl_trigger();   // the next kernel of the stream may be scheduled (it waits for this grid before reading)
   const long long total = static_cast<long long>(B) * gd * gh * 4 * gw;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(256) patch_gather444_kernel(const InT* __restr
 // pad (models/swin_transformer_3d.py:457-461) when dst is larger, crop (:508) when smaller.
 __global__ void grid_copy_kernel(const float* __restrict__ src, int sD, int sH, int sW, float* __restrict__ dst,
                                  int dD, int dH, int dW, int B, int C4) {
+  pdl_trigger();   // the next kernel of the stream may be scheduled (it waits for this grid before reading)
   const long long total = static_cast<long long>(B) * dD * dH * dW * C4;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
@@ -126,6 +128,7 @@ __global__ void grid_copy_kernel(const float* __restrict__ src, int sD, int sH, 
 template <bool SCATTER>
 __global__ void merge_gather_kernel(float* __restrict__ x, int pD, int pH, int pW, int rD, int rH, int rW,
                                     float* __restrict__ out, int oD, int oH, int oW, int B, int C4) {
+  pdl_trigger();   // the next kernel of the stream may be scheduled (it waits for this grid before reading)
   const long long total = static_cast<long long>(B) * oD * oH * oW * 8 * C4;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
@@ -155,6 +158,7 @@ __global__ void merge_gather_kernel(float* __restrict__ x, int pD, int pH, int p
 // dst_bf16[r, c] = src_f32[r, c] * row_scale[r / rows_per_group]
 __global__ void cast_rows_kernel(const float* __restrict__ src, bf16* __restrict__ dst, const float* __restrict__ scale,
                                  int rows_per_group, long long rows, int C4) {
+  pdl_trigger();   // the next kernel of the stream may be scheduled (it waits for this grid before reading)
   const long long total = rows * C4;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {

@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const float* __re
                                                                long long ldy, float* __restrict__ mean_out,
                                                                float* __restrict__ rstd_out, long long rows, int C,
                                                                float eps) {
+  pdl_trigger();   // the next kernel of the stream may be scheduled (it waits for this grid before reading)
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const DyT* __rest
                                                                bf16* __restrict__ dx_bf16, long long ldb,
                                                                const float* __restrict__ row_scale,
                                                                int rows_per_group, long long rows, int C) {
+  pdl_trigger();   // the next kernel of the stream may be scheduled (it waits for this grid before reading)
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -200,6 +202,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_fast_kernel(const float*
                                                                     const float* __restrict__ beta, OutT* __restrict__ y,
                                                                     long long ldy, float* __restrict__ mean_out,
                                                                     float* __restrict__ rstd_out, long long rows, float eps) {
+  pdl_trigger();   // the next kernel of the stream may be scheduled (it waits for this grid before reading)
   constexpr int C = LPR * V * 4;
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, l = lane % LPR;
@@ -260,6 +263,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_fast_kernel(const DyT* _
                                                                     const float* __restrict__ row_scale,
                                                                     int rows_per_group, long long rows,
                                                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_trigger();   // the next kernel of the stream may be scheduled (it waits for this grid before reading)
   constexpr int C = LPR * V * 4;
   constexpr int RPW = 32 / LPR;
   __shared__ float red[LN_WARPS][C + 4];

@@ -193,6 +193,7 @@ __device__ __forceinline__ void add_bias(uint32_t* x, const uint8_t* tab, int ro
 
 template <int WD, int WH, int WW, int VAR>
 __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttnArgs p) {
+  pdl_trigger();   // the next kernel of the stream may be scheduled (it waits for this grid before reading)
   using SM = FwdSmem<WD, WH, WW>;
   using BT = BiasTab<WD, WH, WW>;
   constexpr int N = WD * WH * WW;
@@ -579,6 +580,7 @@ __device__ unsigned long long* g_bwd_timing = nullptr;   // [gridDim][16]
 
 template <int WD, int WH, int WW>
 __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttnArgs p, const float* __restrict__ delta_g) {
+  pdl_trigger();   // the next kernel of the stream may be scheduled (it waits for this grid before reading)
   using SM = BwdSmem<WD, WH, WW>;
   constexpr int N = WD * WH * WW;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -966,6 +968,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
 // also zeroes the Q block of dqkv
 template <int WD, int WH, int WW>
 __global__ void __launch_bounds__(256) wattn_delta_kernel(const WinAttnArgs p, float* __restrict__ delta) {
+  pdl_trigger();   // the next kernel of the stream may be scheduled (it waits for this grid before reading)
   constexpr int N = WD * WH * WW;
   const int s = blockIdx.x;
   const WinCoord wc = win_coord(p, s, WD, WH, WW);
