@@ -89,6 +89,26 @@ def test_gemm_gelu_epilogue_accuracy_wide_range():
     assert rel_err(dx.float(), a.grad) < 5e-3
 
 
+@pytest.mark.parametrize("M,N,K", [(3000, 384, 1536), (1100, 1152, 384), (16128, 384, 384), (257, 768, 192)])
+def test_gemm_cta_pairs(M, N, K):
+    """Shapes with N, K >= 192 run on CTA pairs (cta_group::2, 256-row tiles): odd numbers of 128-row tiles (the
+    peer's half tile lies below the matrix), every store epilogue, K-major and MN-major B operands."""
+    ops = _ops()
+    x, w, b = _bf(_rand(M, K, seed=1)), _bf(_rand(N, K, seed=2, scale=K ** -0.5)), _rand(N, seed=3)
+    pre = x.float() @ w.float().t() + b
+    assert rel_err(ops.linear_fwd(x, w, b).float(), pre) < BF16_TOL
+    resid = _rand(M, N, seed=4)
+    assert rel_err(ops.linear_fwd(x, w, b, out_dtype=torch.float32, resid=resid), resid + pre) < 1e-5
+    aux = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    y = ops.linear_fwd(x, w, b, gelu_aux=aux)
+    assert rel_err(aux.float(), pre) < BF16_TOL
+    assert rel_err(y.float(), torch.nn.functional.gelu(aux.float())) < BF16_TOL
+    if N % 128 == 0:                       # MN-major B halves are whole 64-column boxes
+        dy = _bf(_rand(M, K, seed=5))
+        w2 = _bf(_rand(K, N, seed=6, scale=N ** -0.5))
+        assert rel_err(ops.linear_dgrad(dy, w2).float(), dy.float() @ w2.float()) < BF16_TOL
+
+
 @pytest.mark.parametrize("M,N,K", [(512, 96, 96), (3000, 288, 96), (1000, 96, 384), (700, 384, 96),
                                    (5000, 192, 768), (64, 96, 64), (100, 1536, 384)])
 def test_gemm_dgrad_wgrad(M, N, K):

@@ -170,3 +170,39 @@ def test_in_kernel_gradient_accumulation_matches_autograd():
     ref, got = run(False), run(True)
     for k in ref:
         assert rel_err(got[k], ref[k]) < 1e-4, k
+
+
+def test_droppath_factors_one_draw():
+    """Training forward without forced masks: the DropPath factors of all blocks come from one Bernoulli draw and
+    every factor is 0 or 1/keep of its block (timm DropPath semantics, models/swin_transformer_3d.py:251)."""
+    swin_model, _ = _models()
+    from vsn_b200 import swin
+    case = SWIN_CASES["swin_small_even"]
+    kw = dict(swin_ctor_kwargs(case))
+    kw["stochastic_depth_prob"] = 0.3
+    model = swin_model.SwinTransformerT(**kw).cuda().train()
+    x = torch.from_numpy(synth_volume(case["input"], seed=3)).cuda()
+    seen = []
+    orig = swin.SwinBlockFn.apply
+
+    def spy(*args):
+        seen.append(args[-1])
+        return orig(*args)
+
+    swin.SwinBlockFn.apply = spy
+    try:
+        torch.manual_seed(0)
+        model(x).sum().backward()
+    finally:
+        swin.SwinBlockFn.apply = orig
+    probs = [blk.drop_path.drop_prob if isinstance(blk.drop_path, swin_model.DropPath) else 0.0
+             for layer in model.backbone.layers for blk in layer.blocks]
+    assert len(seen) == len(probs) and any(q > 0 for q in probs)
+    for cfg, q in zip(seen, probs):
+        if q == 0.0:
+            assert cfg.scale1 is None and cfg.scale2 is None
+            continue
+        for sc in (cfg.scale1, cfg.scale2):
+            assert sc.shape == (x.shape[0],) and sc.is_contiguous()
+            ok = (sc == 0) | ((sc - 1.0 / (1.0 - q)).abs() < 1e-6)
+            assert bool(ok.all())
