@@ -40,35 +40,6 @@ struct TokenGeom {
   int lin;      // relative-position linear code of the token inside its window
 };
 
-// token i of window s (window_partition order) -> source row after the cyclic shift, region code, lin code
-__device__ __forceinline__ TokenGeom token_geom(const WinAttnArgs& p, int s, int i) {
-  const int nW = p.nWd * p.nWh * p.nWw;
-  const int b = s / nW, wi = s - b * nW;
-  const int wa = wi / (p.nWh * p.nWw), wr = wi - wa * (p.nWh * p.nWw), wb = wr / p.nWw, wc = wr - wb * p.nWw;
-  const int ld = i / (p.wh * p.ww), lr = i - ld * (p.wh * p.ww), lh = lr / p.ww, lw = lr - lh * p.ww;
-  const int dd = wa * p.wd + ld, hh = wb * p.wh + lh, wv = wc * p.ww + lw;   // position on the rolled grid
-  int d0 = dd + p.sd; if (d0 >= p.Dp) d0 -= p.Dp;                            // torch.roll(-shift) source
-  int h0 = hh + p.sh; if (h0 >= p.Hp) h0 -= p.Hp;
-  int w0 = wv + p.sw; if (w0 >= p.Wp) w0 -= p.Wp;
-  TokenGeom g;
-  g.row = ((b * p.Dp + d0) * p.Hp + h0) * p.Wp + w0;
-  const int rd = dd < p.Dp - p.wd ? 0 : (dd < p.Dp - p.sd ? 1 : 2);
-  const int rh = hh < p.Hp - p.wh ? 0 : (hh < p.Hp - p.sh ? 1 : 2);
-  const int rw = wv < p.Wp - p.ww ? 0 : (wv < p.Wp - p.sw ? 1 : 2);
-  g.code = 9 * rd + 3 * rh + rw;
-  g.lin = ld * ((2 * p.wh - 1) * (2 * p.ww - 1)) + lh * (2 * p.ww - 1) + lw;
-  return g;
-}
-
-// windows that straddle a region boundary are exactly the last ones along an axis
-__device__ __forceinline__ bool window_masked(const WinAttnArgs& p, int s) {
-  if (!p.use_mask) return false;
-  const int nW = p.nWd * p.nWh * p.nWw;
-  const int wi = s % nW;
-  const int wa = wi / (p.nWh * p.nWw), wr = wi - wa * (p.nWh * p.nWw), wb = wr / p.nWw, wc = wr - wb * p.nWw;
-  return (p.sd > 0 && wa == p.nWd - 1) || (p.sh > 0 && wb == p.nWh - 1) || (p.sw > 0 && wc == p.nWw - 1);
-}
-
 // Relative-position bias in smem, window dims static: row ((a*(2WH-1) + b)*WW + wi) holds the 16-byte vector
 // { table[(a, b, wi - wj + WW-1), head] * log2(e) : wj = 0..WW-1 } as bf16, with a = di-dj+WD-1, b = hi-hj+WH-1.
 // For query token i=(di,hi,wi) and the key row kr=(dj,hj) of the window the vector sits at row
