@@ -665,6 +665,24 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
       const uint64_t desc_ds = tc::make_smem_desc_sw128(tc::smem_u32(ds_tile), 16384, 1024);
       const uint64_t desc_st0 = tc::make_smem_desc_sw64(tc::smem_u32(stages), 16, 512);   // stage 0, offset 0
       long long tm_ld = 0, tm_pr = 0, tm_acc = 0, tm_t0 = TCLK(), tq;
+      int pend_mb = -1, pend_st = 0;
+      uint64_t pend_dst = 0;
+      auto issue_dq = [&]() {
+        if (pend_mb < 0) return;
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            tc::mma_bf16_ss(tmem_base + COL_DQ + pend_mb * 32, tc::desc_advance(desc_ds, pend_mb * 32768 + k * 2048),
+                            tc::desc_advance(pend_dst, 32768 + k * 1024), idesc_q, k);
+          tc::mma_commit(&ds_free[pend_mb]);
+          if (pend_mb == 1) {
+            tc::mma_commit(unit_done);
+            tc::mma_commit(&ld_empty[pend_st]);
+          }
+        }
+        __syncwarp();
+        pend_mb = -1;
+      };
       for (int T = 0; T <= TT; ++T) {
         if (T < TT) {
           const int n = T / NSUB, t = T % NSUB, st = n & 1, b = T & 1;
@@ -687,6 +705,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
           }
           __syncwarp();
         }
+        issue_dq();
         if (T >= 1) {
           const int V = T - 1, n = V / NSUB, t = V % NSUB, st = n & 1, b = V & 1;
           tq = TCLK();
@@ -710,23 +729,14 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
               tc::mma_bf16_ts(tmem_base + t * QS + k * 16, a_ds + k * 16, desc_ident, idesc_b, n ? 1u : 0u);
             }
             if (t == NSUB - 1) tc::mma_commit(kv_done);
-            if ((t & 3) == 3) {
-              // dQ for the 128-query block that is now complete in the smem tile
-              const int mb = t >> 2;
-#pragma unroll
-              for (int k = 0; k < 8; ++k)
-                tc::mma_bf16_ss(tmem_base + COL_DQ + mb * 32, tc::desc_advance(desc_ds, mb * 32768 + k * 2048),
-                                tc::desc_advance(dst, 32768 + k * 1024), idesc_q, k);
-              tc::mma_commit(&ds_free[mb]);
-              if (mb == 1) {
-                tc::mma_commit(unit_done);
-                tc::mma_commit(&ld_empty[st]);
-              }
-            }
           }
           __syncwarp();
+          // dQ for the 128-query block that is now complete in the smem tile: eight K=16 steps that nobody waits for
+          // soon -- issued in the next iteration, behind that sub-tile's S^T / dP^T (the tensor pipe runs in order)
+          if ((t & 3) == 3) { pend_mb = t >> 2; pend_dst = dst; pend_st = st; }
         }
       }
+      issue_dq();
       if (g_bwd_timing != nullptr && lane == 0) {
         unsigned long long* o = g_bwd_timing + ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16;
         o[0] = TCLK() - tm_t0; o[1] = tm_ld; o[2] = tm_pr; o[3] = tm_acc; o[4] = TT;
