@@ -2,6 +2,7 @@
 // Replaces nn.LayerNorm on the path: norm1/norm2 (models/swin_transformer_3d.py:236,255,330,373),
 // PatchEmbed3D.norm (:541), PatchMerging.norm (:570), backbone.norm (:693), and the ViT norms
 // (models/vit_3d.py:69,98,371,373,401).  eps = 1e-5, biased variance, statistics in fp32.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -459,7 +460,11 @@ extern "C" int vsn_layernorm_bwd(const void* dy, long long lddy, int dy_bf16, co
   const LnShape fs = ln_fast_shape(C);
   if (fs.lpr != 0 && lddy % 4 == 0 && ldx % 4 == 0) {
     const long long need = ceil_div_ll(rows, LN_WARPS * (32 / fs.lpr));
-    const long long cap = 4LL * vsn_num_sms();
+    // every block ends with one atomic per column for dgamma / dbeta: short problems (the late stages) take fewer,
+    // longer blocks so that those atomics do not outweigh the row work
+    static int cap_small = -1;
+    if (cap_small < 0) { const char* e = getenv("VSN_LN_BWD_CAP"); cap_small = e ? atoi(e) : 2; }
+    const long long cap = (rows * C < (1LL << 25) ? cap_small : 4) * static_cast<long long>(vsn_num_sms());
     const unsigned g2 = static_cast<unsigned>(need < cap ? need : cap);
 #define VSN_LN_BWD(L, VV)                                                                                          \
     if (fs.lpr == L && fs.v == VV) {                                                                                 \
