@@ -101,18 +101,22 @@ __global__ void __launch_bounds__(256) patch_gather444_kernel(const InT* __restr
 
 // Copy the overlapping box of two channels-last grids and zero-fill the rest of dst.
 // pad (models/swin_transformer_3d.py:457-461) when dst is larger, crop (:508) when smaller.
+template <typename IdxT>
 __global__ void grid_copy_kernel(const float* __restrict__ src, int sD, int sH, int sW, float* __restrict__ dst,
                                  int dD, int dH, int dW, int B, int C4) {
   pdl_trigger();   // the next kernel of the stream may be scheduled (it waits for this grid before reading)
-  const long long total = static_cast<long long>(B) * dD * dH * dW * C4;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-    long long t = idx;
-    const int c = static_cast<int>(t % C4); t /= C4;
-    const int w = static_cast<int>(t % dW); t /= dW;
-    const int h = static_cast<int>(t % dH); t /= dH;
-    const int d = static_cast<int>(t % dD); t /= dD;
-    const int b = static_cast<int>(t);
+  const IdxT total = static_cast<IdxT>(B) * dD * dH * dW * C4;
+  const IdxT stride = static_cast<IdxT>(gridDim.x) * blockDim.x;
+  for (IdxT idx = static_cast<IdxT>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    IdxT t = idx / static_cast<IdxT>(C4);
+    const int c = static_cast<int>(idx - t * static_cast<IdxT>(C4));
+    IdxT u = t / static_cast<IdxT>(dW);
+    const int w = static_cast<int>(t - u * static_cast<IdxT>(dW)); t = u;
+    u = t / static_cast<IdxT>(dH);
+    const int h = static_cast<int>(t - u * static_cast<IdxT>(dH)); t = u;
+    u = t / static_cast<IdxT>(dD);
+    const int d = static_cast<int>(t - u * static_cast<IdxT>(dD));
+    const int b = static_cast<int>(u);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (d < sD && h < sH && w < sW)
       v = reinterpret_cast<const float4*>(src)[(((static_cast<long long>(b) * sD + d) * sH + h) * sW + w) * C4 + c];
@@ -125,20 +129,25 @@ __global__ void grid_copy_kernel(const float* __restrict__ src, int sD, int sH, 
 // outside the REAL grid (rD,rH,rW) read as zero (crop + odd pad); x lives on the padded stage grid (pD,pH,pW).
 // scatter=true runs the same index map backwards (gradient): x[...] = out[...], untouched positions keep
 // their (pre-zeroed) value.
-template <bool SCATTER>
+// IdxT = unsigned (problems below 2^31 float4 elements, i.e. all of them in practice): the index decomposition is
+// four 32-bit divisions instead of six 64-bit ones, which were costing more than the two memory accesses they address.
+template <bool SCATTER, typename IdxT>
 __global__ void merge_gather_kernel(float* __restrict__ x, int pD, int pH, int pW, int rD, int rH, int rW,
                                     float* __restrict__ out, int oD, int oH, int oW, int B, int C4) {
   pdl_trigger();   // the next kernel of the stream may be scheduled (it waits for this grid before reading)
-  const long long total = static_cast<long long>(B) * oD * oH * oW * 8 * C4;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-    long long t = idx;
-    const int c = static_cast<int>(t % C4); t /= C4;
-    const int q = static_cast<int>(t % 8); t /= 8;
-    const int w = static_cast<int>(t % oW); t /= oW;
-    const int h = static_cast<int>(t % oH); t /= oH;
-    const int d = static_cast<int>(t % oD); t /= oD;
-    const int b = static_cast<int>(t);
+  const IdxT total = static_cast<IdxT>(B) * oD * oH * oW * 8 * C4;
+  const IdxT stride = static_cast<IdxT>(gridDim.x) * blockDim.x;
+  for (IdxT idx = static_cast<IdxT>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    IdxT t = idx / static_cast<IdxT>(C4);
+    const int c = static_cast<int>(idx - t * static_cast<IdxT>(C4));
+    const int q = static_cast<int>(t & 7); t >>= 3;
+    IdxT u = t / static_cast<IdxT>(oW);
+    const int w = static_cast<int>(t - u * static_cast<IdxT>(oW)); t = u;
+    u = t / static_cast<IdxT>(oH);
+    const int h = static_cast<int>(t - u * static_cast<IdxT>(oH)); t = u;
+    u = t / static_cast<IdxT>(oD);
+    const int d = static_cast<int>(t - u * static_cast<IdxT>(oD));
+    const int b = static_cast<int>(u);
     // q -> (od, oh, ow) in the reference's concatenation order
     const int od = (0xB2 >> q) & 1;  // q: 0 1 2 3 4 5 6 7 -> 0 1 0 0 1 1 0 1
     const int oh = (0xD4 >> q) & 1;  //                    -> 0 0 1 0 1 0 1 1
@@ -310,7 +319,11 @@ extern "C" int vsn_grid_copy(const float* src, int sD, int sH, int sW, float* ds
   VSN_CHECK(C % 4 == 0, "vsn_grid_copy: C must be a multiple of 4");
   const long long total = static_cast<long long>(B) * dD * dH * dW * (C / 4);
   if (total == 0) return 0;
-  grid_copy_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, sD, sH, sW, dst, dD,
+  if (total + 256LL * grid_for(total, 256) < (1LL << 31))
+    grid_copy_kernel<unsigned><<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, sD, sH, sW, dst, dD,
+                                                                                            dH, dW, B, C / 4);
+  else
+    grid_copy_kernel<long long><<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, sD, sH, sW, dst, dD,
                                                                                             dH, dW, B, C / 4);
   VSN_LAUNCH_CHECK();
   return 0;
@@ -323,10 +336,15 @@ extern "C" int vsn_merge_gather(float* x, int pD, int pH, int pW, int rD, int rH
   const long long total = static_cast<long long>(B) * oD * oH * oW * 8 * (C / 4);
   if (total == 0) return 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (scatter)
-    merge_gather_kernel<true><<<grid_for(total, 256), 256, 0, s>>>(x, pD, pH, pW, rD, rH, rW, out, oD, oH, oW, B, C / 4);
+  const bool small = total + 256LL * grid_for(total, 256) < (1LL << 31);     // index + grid stride fit 32 bits
+  if (scatter && small)
+    merge_gather_kernel<true, unsigned><<<grid_for(total, 256), 256, 0, s>>>(x, pD, pH, pW, rD, rH, rW, out, oD, oH, oW, B, C / 4);
+  else if (scatter)
+    merge_gather_kernel<true, long long><<<grid_for(total, 256), 256, 0, s>>>(x, pD, pH, pW, rD, rH, rW, out, oD, oH, oW, B, C / 4);
+  else if (small)
+    merge_gather_kernel<false, unsigned><<<grid_for(total, 256), 256, 0, s>>>(x, pD, pH, pW, rD, rH, rW, out, oD, oH, oW, B, C / 4);
   else
-    merge_gather_kernel<false><<<grid_for(total, 256), 256, 0, s>>>(x, pD, pH, pW, rD, rH, rW, out, oD, oH, oW, B, C / 4);
+    merge_gather_kernel<false, long long><<<grid_for(total, 256), 256, 0, s>>>(x, pD, pH, pW, rD, rH, rW, out, oD, oH, oW, B, C / 4);
   VSN_LAUNCH_CHECK();
   return 0;
 }

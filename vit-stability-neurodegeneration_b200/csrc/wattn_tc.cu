@@ -25,7 +25,8 @@ namespace {
 constexpr int NP = 256;                    // padded tokens per window
 constexpr int HD = 32;
 constexpr int TILE_BYTES = NP * HD * 2;    // 16 KB
-constexpr int STAGE_BYTES = 3 * TILE_BYTES;
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;   // Q | K | V | one-hot region codes (forward kernel)
+constexpr float REGION_ONE = 24.0f;          // one-hot value: REGION_ONE^2 * scale = 576 * 32^-1/2 = 101.8 nats, the reference's 100
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float MASK_L2E = -100.0f * LOG2E;
 constexpr float PAD_BIAS = -30000.0f;      // keys >= N
@@ -171,7 +172,6 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* stages = smem;
   uint8_t* bias_s = smem + SM::BIAS;
-  uint8_t* keycode = smem + SM::KEYCODE;
   int* rowidx = reinterpret_cast<int*>(smem + SM::ROWIDX);        // written by the loader with the tiles
   int* winmask = rowidx + FWD_STAGES * NP;
   float2* stats = reinterpret_cast<float2*>(smem + SM::STATS);    // (local max, local sum)
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
   if (warp == SM_WARPS + 1) tc::tmem_alloc(tmem_slot, 512);
   BT::build(p, head, bias_s);
   // rows N..255 of every tile stay zero for the whole kernel (the loader only writes rows < N)
-  for (int idx = threadIdx.x; idx < FWD_STAGES * 3 * (NP - N) * 4; idx += blockDim.x) {
+  for (int idx = threadIdx.x; idx < FWD_STAGES * 4 * (NP - N) * 4; idx += blockDim.x) {
     const int tile = idx / ((NP - N) * 4), rem = idx - tile * ((NP - N) * 4);
     const int row = N + rem / 4, c = rem & 3;
     *reinterpret_cast<uint4*>(stages + tile * TILE_BYTES + swz64(row, c)) = make_uint4(0, 0, 0, 0);
@@ -231,8 +231,19 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
       const WinCoord wc = win_coord(p, s, WD, WH, WW);
       for (int i = lane; i < N; i += 32) {
         const TokenGeom g = token_geom_w<WD, WH, WW>(p, wc, i);
-        keycode[st * NP + i] = static_cast<uint8_t>(g.code);
         rowidx[st * NP + i] = g.row;
+        if (wc.masked()) {
+          // shift mask on the tensor cores: E[i][c] = REGION_ONE where c is the region of token i, so that
+          // (E E^T)[i][j] = REGION_ONE^2 for tokens of the same region, 0 otherwise -- added to Q K^T by two more K=16
+          // steps.  The reference adds -100 to pairs of DIFFERENT regions (models/swin_transformer_3d.py:463-492);
+          // softmax is invariant under the per-row constant that separates the two forms.
+          uint32_t w[4] = {0u, 0u, 0u, 0u};
+          w[(g.code & 7) >> 1] = (g.code & 1) ? 0x41C00000u : 0x000041C0u;     // bf16 24.0 in the pair's high / low half
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<uint4*>(sq + 3 * TILE_BYTES + swz64(i, c)) =
+                c == (g.code >> 3) ? make_uint4(w[0], w[1], w[2], w[3]) : make_uint4(0u, 0u, 0u, 0u);
+        }
         const bf16* src = p.qkv + g.row * ld + head * HD;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -261,11 +272,19 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
           tc::fence_after_sync();
           const uint64_t dq = tc::desc_advance(desc_st0, st * STAGE_BYTES + h * (128 * 64));
           const uint64_t dk = tc::desc_advance(desc_st0, st * STAGE_BYTES + TILE_BYTES);
+          const bool win_masked = winmask[st] != 0;
           if (tc::elect_one()) {
 #pragma unroll
             for (int k = 0; k < HD / 16; ++k)
               tc::mma_bf16_ss(tmem_base + h * NP, tc::desc_advance(dq, k * 32), tc::desc_advance(dk, k * 32), idesc_s,
                               k > 0 ? 1u : 0u);
+            if (win_masked) {        // + E_h E^T: the shift mask
+              const uint64_t de = tc::desc_advance(desc_st0, st * STAGE_BYTES + 3 * TILE_BYTES);
+#pragma unroll
+              for (int k = 0; k < 2; ++k)
+                tc::mma_bf16_ss(tmem_base + h * NP, tc::desc_advance(de, h * (128 * 64) + k * 32),
+                                tc::desc_advance(de, k * 32), idesc_s, 1u);
+            }
             tc::mma_commit(&s_full[h]);
           }
           __syncwarp();
@@ -312,9 +331,10 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
       tc::mbar_wait(&s_full[h], it & 1);
       tc::fence_after_sync();
       // geometry of the window as the loader worked it out (stage st is not refilled before this unit's P V ran)
-      const uint32_t cq4 = static_cast<uint32_t>(keycode[st * NP + ib]) * 0x01010101u;
       const int out_row = rowidx[st * NP + ib];
-      const bool masked = winmask[st] != 0;
+      // masked windows carry REGION_ONE^2 * cscale on every same-region logit (the row maximum is one of them): taken
+      // out of the stored log-sum-exp, which the backward kernel combines with the reference's -100 form
+      const float lse_off = winmask[st] != 0 ? REGION_ONE * REGION_ONE * cscale : 0.f;
 #pragma unroll
       for (int pass = 0; pass < 2; ++pass) {
         const int part = 2 * pass + ch;
@@ -331,23 +351,6 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
         } else {
           if (ch == 0) add_bias<WD, WH, WW, 2>(x, bias_s, rowbase, cscale);
           else add_bias<WD, WH, WW, 3>(x, bias_s, rowbase, cscale);
-        }
-        if (masked) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint4 kc = *reinterpret_cast<const uint4*>(keycode + st * NP + part * 64 + c * 16);
-            const uint32_t kw[4] = {kc.x, kc.y, kc.z, kc.w};
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const uint32_t ne = __vcmpne4(kw[t], cq4);
-#pragma unroll
-              for (int b = 0; b < 4; ++b) {
-                const uint32_t m32 = __byte_perm(ne, 0, 0x8888u | (0x1111u * b));
-                const int k = c * 16 + t * 4 + b;
-                x[k] = __float_as_uint(__uint_as_float(x[k]) + __uint_as_float(m32 & __float_as_uint(MASK_L2E)));
-              }
-            }
-          }
         }
         float mx0 = -3.0e38f, mx1 = -3.0e38f;
 #pragma unroll
@@ -420,7 +423,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
         st_global_v8(p.out + static_cast<long long>(out_row) * p.C + head * HD + ch * 16, w);
       }
       if (ch == 0 && p.lse != nullptr)
-        p.lse[(static_cast<long long>(s) * p.heads + head) * NP + i] = m + log2f(l);   // log2 domain (consumed by wattn_bwd_kernel)
+        p.lse[(static_cast<long long>(s) * p.heads + head) * NP + i] = m + log2f(l) - lse_off;   // log2 domain (consumed by wattn_bwd_kernel)
     }
   }
   tc::fence_before_sync();
