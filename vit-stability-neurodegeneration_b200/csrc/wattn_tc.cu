@@ -25,7 +25,7 @@ namespace {
 constexpr int NP = 256;                    // padded tokens per window
 constexpr int HD = 32;
 constexpr int TILE_BYTES = NP * HD * 2;    // 16 KB
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;   // Q | K | V | one-hot region codes (forward kernel)
+constexpr int STAGE_BYTES = 3 * TILE_BYTES;   // Q | K | V (forward kernel; the one-hot region tile follows the ring)
 constexpr float REGION_ONE = 24.0f;          // one-hot value: REGION_ONE^2 * scale = 576 * 32^-1/2 = 101.8 nats, the reference's 100
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float MASK_L2E = -100.0f * LOG2E;
@@ -119,7 +119,8 @@ constexpr int FWD_STAGES = 2;
 
 template <int WD, int WH, int WW>
 struct FwdSmem {
-  static constexpr int BIAS = FWD_STAGES * STAGE_BYTES;
+  static constexpr int ONEHOT = FWD_STAGES * STAGE_BYTES;      // one tile, shared by the two stages (see the loader)
+  static constexpr int BIAS = ONEHOT + TILE_BYTES;
   static constexpr int KEYCODE = BIAS + BiasTab<WD, WH, WW>::BYTES;
   static constexpr int ROWIDX = KEYCODE + FWD_STAGES * NP;     // int [2][256] source row of every token + [2] masked flag
   static constexpr int STATS = ROWIDX + FWD_STAGES * NP * 4 + 16;   // float2 [2][4 parts][128]
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
   if (warp == SM_WARPS + 1) tc::tmem_alloc(tmem_slot, 512);
   BT::build(p, head, bias_s);
   // rows N..255 of every tile stay zero for the whole kernel (the loader only writes rows < N)
-  for (int idx = threadIdx.x; idx < FWD_STAGES * 4 * (NP - N) * 4; idx += blockDim.x) {
+  for (int idx = threadIdx.x; idx < (FWD_STAGES * 3 + 1) * (NP - N) * 4; idx += blockDim.x) {
     const int tile = idx / ((NP - N) * 4), rem = idx - tile * ((NP - N) * 4);
     const int row = N + rem / 4, c = rem & 3;
     *reinterpret_cast<uint4*>(stages + tile * TILE_BYTES + swz64(row, c)) = make_uint4(0, 0, 0, 0);
@@ -232,18 +233,6 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
       for (int i = lane; i < N; i += 32) {
         const TokenGeom g = token_geom_w<WD, WH, WW>(p, wc, i);
         rowidx[st * NP + i] = g.row;
-        if (wc.masked()) {
-          // shift mask on the tensor cores: E[i][c] = REGION_ONE where c is the region of token i, so that
-          // (E E^T)[i][j] = REGION_ONE^2 for tokens of the same region, 0 otherwise -- added to Q K^T by two more K=16
-          // steps.  The reference adds -100 to pairs of DIFFERENT regions (models/swin_transformer_3d.py:463-492);
-          // softmax is invariant under the per-row constant that separates the two forms.
-          uint32_t w[4] = {0u, 0u, 0u, 0u};
-          w[(g.code & 7) >> 1] = (g.code & 1) ? 0x41C00000u : 0x000041C0u;     // bf16 24.0 in the pair's high / low half
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            *reinterpret_cast<uint4*>(sq + 3 * TILE_BYTES + swz64(i, c)) =
-                c == (g.code >> 3) ? make_uint4(w[0], w[1], w[2], w[3]) : make_uint4(0u, 0u, 0u, 0u);
-        }
         const bf16* src = p.qkv + g.row * ld + head * HD;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -251,6 +240,25 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
           tc::cp_async16(sq + o, src + c * 8);
           tc::cp_async16(sq + TILE_BYTES + o, src + p.C + c * 8);
           tc::cp_async16(sq + 2 * TILE_BYTES + o, src + 2 * p.C + c * 8);
+        }
+      }
+      if (wc.masked()) {
+        // shift mask on the tensor cores: E[i][c] = REGION_ONE where c is the region of token i, so that
+        // (E E^T)[i][j] = REGION_ONE^2 for tokens of the same region, 0 otherwise -- added to Q K^T by two more K=16
+        // steps.  The reference adds -100 to pairs of DIFFERENT regions (models/swin_transformer_3d.py:463-492);
+        // softmax is invariant under the per-row constant that separates the two forms.
+        // The tile is not double-buffered: the S MMAs of the previous window (its second query half last) must have
+        // read it -- they retire while this window's Q / K / V are still in flight.
+        if (it > 0) tc::mbar_wait(&s_full[1], (it - 1) & 1);
+        uint8_t* onehot = stages + FWD_STAGES * STAGE_BYTES;
+        for (int i = lane; i < N; i += 32) {
+          const int code = token_geom_w<WD, WH, WW>(p, wc, i).code;
+          uint32_t w[4] = {0u, 0u, 0u, 0u};
+          w[(code & 7) >> 1] = (code & 1) ? 0x41C00000u : 0x000041C0u;     // bf16 24.0 in the pair's high / low half
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<uint4*>(onehot + swz64(i, c)) =
+                c == (code >> 3) ? make_uint4(w[0], w[1], w[2], w[3]) : make_uint4(0u, 0u, 0u, 0u);
         }
       }
       if (lane == 0) winmask[st] = wc.masked() ? 1 : 0;
@@ -279,7 +287,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
               tc::mma_bf16_ss(tmem_base + h * NP, tc::desc_advance(dq, k * 32), tc::desc_advance(dk, k * 32), idesc_s,
                               k > 0 ? 1u : 0u);
             if (win_masked) {        // + E_h E^T: the shift mask
-              const uint64_t de = tc::desc_advance(desc_st0, st * STAGE_BYTES + 3 * TILE_BYTES);
+              const uint64_t de = tc::desc_advance(desc_st0, FWD_STAGES * STAGE_BYTES);
 #pragma unroll
               for (int k = 0; k < 2; ++k)
                 tc::mma_bf16_ss(tmem_base + h * NP, tc::desc_advance(de, h * (128 * 64) + k * 32),
