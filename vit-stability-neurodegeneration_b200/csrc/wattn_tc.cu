@@ -114,7 +114,7 @@ __device__ __forceinline__ TokenGeom token_geom_t(const WinAttnArgs& p, int s, i
 
 // =========================================== forward ==============================================
 constexpr int SM_WARPS = 16;                      // softmax warps: 4 TMEM lane quadrants x 4 column parts
-constexpr int FWD_THREADS = (SM_WARPS + 2) * 32;  // + loader warp + MMA warp
+constexpr int FWD_THREADS = (SM_WARPS + 4) * 32;  // + one warpgroup of helpers: loader warp, MMA warp, two idle
 constexpr int FWD_STAGES = 2;
 
 template <int WD, int WH, int WW>
@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* stages = smem;
   uint8_t* bias_s = smem + SM::BIAS;
+  uint8_t* keycode = smem + SM::KEYCODE;                            // loader scratch: region code of every token
   int* rowidx = reinterpret_cast<int*>(smem + SM::ROWIDX);        // written by the loader with the tiles
   int* winmask = rowidx + FWD_STAGES * NP;
   float2* stats = reinterpret_cast<float2*>(smem + SM::STATS);    // (local max, local sum)
@@ -221,6 +222,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Register budget: the launch gives every thread 96 registers; the helper warpgroup hands most of its share back
+  // and the softmax warpgroups grow to 104 (they hold 64 logits each and were spilling).
+  // (each role's code sits inside the branch of its own setmaxnreg: after a join ptxas allocates for the lower limit)
+  if (warp >= SM_WARPS) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == SM_WARPS) {
     // ------------------------------------------------------------------ loader
     const long long ld = 3LL * p.C;
@@ -233,6 +239,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
       for (int i = lane; i < N; i += 32) {
         const TokenGeom g = token_geom_w<WD, WH, WW>(p, wc, i);
         rowidx[st * NP + i] = g.row;
+        keycode[i] = static_cast<uint8_t>(g.code);      // (this lane reads it back below)
         const bf16* src = p.qkv + g.row * ld + head * HD;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -252,7 +259,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
         if (it > 0) tc::mbar_wait(&s_full[1], (it - 1) & 1);
         uint8_t* onehot = stages + FWD_STAGES * STAGE_BYTES;
         for (int i = lane; i < N; i += 32) {
-          const int code = token_geom_w<WD, WH, WW>(p, wc, i).code;
+          const int code = keycode[i];
           uint32_t w[4] = {0u, 0u, 0u, 0u};
           w[(code & 7) >> 1] = (code & 1) ? 0x41C00000u : 0x000041C0u;     // bf16 24.0 in the pair's high / low half
 #pragma unroll
@@ -315,7 +322,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
         }
       }
     }
+  }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     // ------------------------------------------------------------------ softmax + epilogue
     // Two independent groups of 8 warps: group g owns the query half h = g of every window (its own TMEM region,
     // its own barriers), so while one group waits for its MMAs (P V, then the next S) the other one keeps the
