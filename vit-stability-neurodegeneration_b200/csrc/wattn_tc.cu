@@ -495,7 +495,7 @@ int wattn_tc_fwd(const WinAttnArgs& a, cudaStream_t stream) {
 //   dQ is the sum of the two key halves: bf16x2 red.add into the zeroed Q block of dqkv.
 // Warps: 0-7 compute group 0 (even sub-tiles), 8-15 group 1 (odd sub-tiles; also the per-window read-out of
 // dK / dV / dQ), 16 loader, 17 MMA issuer.  Thread = (key row, 16 of the sub-tile's 32 queries).
-constexpr int BWD_THREADS = 18 * 32;
+constexpr int BWD_THREADS = 20 * 32;           // 16 compute warps + one warpgroup of helpers (loader, MMA issuer, two idle)
 constexpr int QS = 32;                         // queries per sub-tile
 constexpr int NSUB = NP / QS;                  // 8
 constexpr int BWD_STAGE_BYTES = 51712;         // Q 16K | dO 16K | K_half 8K | V_half 8K | lse2 1K | delta 1K | qcode 256
@@ -637,6 +637,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Register budget as in the forward kernel: 96 per thread at launch, the helper warpgroup drops to 56 and the
+  // compute warpgroups grow to 104 (each role inside the branch of its own setmaxnreg).
+  if (warp >= 16) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 16) {
     // ------------------------------------------------------------------ loader
     const long long ld = 3LL * p.C;
@@ -762,7 +766,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
         o[0] = TCLK() - tm_t0; o[1] = tm_ld; o[2] = tm_pr; o[3] = tm_acc; o[4] = TT;
       }
     }
+  }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     // ------------------------------------------------------------------ compute groups
     const int g = warp >> 3, q4 = warp & 3, half = (warp >> 2) & 1;
     const int r = q4 * 32 + lane;                  // key row inside the half = TMEM lane
