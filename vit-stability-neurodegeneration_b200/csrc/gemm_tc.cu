@@ -1,8 +1,10 @@
-// bf16 GEMM on the 5th-gen tensor cores: TMA -> 128B-swizzled smem -> tcgen05.mma (fp32 accumulators in
-// TMEM) -> tcgen05.ld -> fused epilogue.  One 128 x BN output tile per CTA, warp-specialised:
-//   warp 0   TMA producer (one elected lane)
-//   warp 1   TMEM allocator + MMA issuer (one elected lane)
-//   warps 2-5 epilogue (each owns the 32 TMEM lanes its warp id maps to)
+// bf16 GEMM on the 5th-gen tensor cores: TMA -> 128B-swizzled smem ring -> tcgen05.mma (fp32 accumulators in
+// TMEM, two buffers) -> tcgen05.ld -> fused epilogue.  Persistent CTAs (one per SM, or one CTA pair per two SMs
+// for cta_group::2 tiles of 256 rows), 128 x BN tiles, warp-specialised:
+//   warp 0    TMA producer (one lane), runs ahead across tile boundaries
+//   warp 1    TMEM allocator + MMA issuer (converged warp, elect.sync)
+//   warps 2.. 8 or 16 epilogue warps (each owns the 32 TMEM lanes its warp id maps to and a share of the columns)
+// Launched with programmatic dependent launch: everything up to the first operand load overlaps the previous kernel.
 //
 // Operand majors cover all three GEMMs of a Linear layer without materialising transposes:
 //   forward  Y[M,N]  = X[M,K]  * W[N,K]^T     A K-major,  B K-major

@@ -5,7 +5,6 @@ computes with torch ops; torch is the allocator and the stream owner.
 """
 from __future__ import annotations
 
-import math
 from typing import Optional, Sequence
 
 import torch
@@ -14,7 +13,6 @@ from . import _lib
 
 BF16 = torch.bfloat16
 F32 = torch.float32
-_N_SMS = 148
 
 
 def _stream() -> int:
