@@ -89,6 +89,32 @@ def test_gemm_gelu_epilogue_accuracy_wide_range():
     assert rel_err(dx.float(), a.grad) < 5e-3
 
 
+@pytest.mark.parametrize("M,N,K", [(20000, 384, 96), (20000, 288, 96), (30000, 96, 96), (20000, 96, 384),
+                                   (26000, 192, 192), (20000, 96, 288)])
+def test_gemm_stationary_resident_weights(M, N, K):
+    """Many row tiles and few column tiles: the n-stationary schedule with the weight tile kept resident in the TMA
+    ring (fetched on the first pass only; the ring is cut to a multiple of the tile's k-blocks), forward epilogues
+    and the MN-major dgrad, with a ragged last row tile."""
+    ops = _ops()
+    M += 37
+    x, w, b = _bf(_rand(M, K, seed=1)), _bf(_rand(N, K, seed=2, scale=K ** -0.5)), _rand(N, seed=3)
+    pre = x.float() @ w.float().t() + b
+    assert rel_err(ops.linear_fwd(x, w, b).float(), pre) < BF16_TOL
+    resid = _rand(M, N, seed=4)
+    assert rel_err(ops.linear_fwd(x, w, b, out_dtype=torch.float32, resid=resid), resid + pre) < 1e-5
+    aux = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    y = ops.linear_fwd(x, w, b, gelu_aux=aux)
+    assert rel_err(aux.float(), pre) < BF16_TOL
+    assert rel_err(y.float(), torch.nn.functional.gelu(aux.float())) < BF16_TOL
+    dy = _bf(_rand(M, K, seed=5))
+    w2 = _bf(_rand(K, N, seed=6, scale=N ** -0.5))
+    assert rel_err(ops.linear_dgrad(dy, w2).float(), dy.float() @ w2.float()) < BF16_TOL
+    dx = ops.linear_dgrad(dy, w2, gelu_aux=aux)
+    a = aux.float().requires_grad_(True)
+    torch.nn.functional.gelu(a).backward(dy.float() @ w2.float())
+    assert rel_err(dx.float(), a.grad) < BF16_TOL
+
+
 @pytest.mark.parametrize("M,N,K", [(3000, 384, 1536), (1100, 1152, 384), (16128, 384, 384), (257, 768, 192)])
 def test_gemm_cta_pairs(M, N, K):
     """Shapes with N, K >= 192 run on CTA pairs (cta_group::2, 256-row tiles): odd numbers of 128-row tiles (the
