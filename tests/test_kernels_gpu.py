@@ -89,6 +89,21 @@ def test_gemm_gelu_epilogue_accuracy_wide_range():
     assert rel_err(dx.float(), a.grad) < 5e-3
 
 
+@pytest.mark.parametrize("T,N,K", [(40037, 384, 96), (40037, 96, 96), (70001, 96, 384), (40037, 288, 96)])
+def test_gemm_wgrad_long_token_axis(T, N, K):
+    """Few output tiles over tens of thousands of tokens: the library picks the reduction split by whole waves of
+    the persistent grid (early-stage wgrads); weight and bias gradients accumulate."""
+    ops = _ops()
+    dy, x = _bf(_rand(T, N, seed=1)), _bf(_rand(T, K, seed=2))
+    ref = dy.float().t() @ x.float()
+    dw, db = torch.zeros(N, K, device="cuda"), torch.zeros(N, device="cuda")
+    ops.linear_wgrad(dy, x, dw, dbias=db)
+    assert rel_err(dw, ref) < 1e-4
+    assert rel_err(db, dy.float().sum(0)) < 1e-4
+    ops.linear_wgrad(dy, x, dw)
+    assert rel_err(dw, 2 * ref) < 1e-4
+
+
 @pytest.mark.parametrize("M,N,K", [(20000, 384, 96), (20000, 288, 96), (30000, 96, 96), (20000, 96, 384),
                                    (26000, 192, 192), (20000, 96, 288)])
 def test_gemm_stationary_resident_weights(M, N, K):
