@@ -228,7 +228,10 @@ def _ref_window_attention(qkv, table, B, grid, window, shift, shifted, heads, hd
 
 
 @pytest.mark.parametrize("grid,heads,shifted", [((12, 14, 12), 2, False), ((12, 14, 12), 2, True),
-                                                ((6, 7, 6), 3, True), ((18, 21, 12), 1, True)])
+                                                ((6, 7, 6), 3, True), ((18, 21, 12), 1, True),
+                                                # several windows per persistent CTA (ring wrap-around, deferred
+                                                # read-outs and MMAs across window boundaries, masked and unmasked mixed)
+                                                ((24, 28, 24), 3, True), ((24, 28, 24), 3, False)])
 def test_window_attention_fwd_bwd(grid, heads, shifted):
     ops = _ops()
     B, window, shift, hd = 2, (6, 7, 6), (3, 3, 3), 32
