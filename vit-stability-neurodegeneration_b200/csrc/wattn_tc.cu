@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
             // keys 64*part .. 64*part+63 were exponentiated against their own local max: one accumulator each
 #pragma unroll
             for (int k = 0; k < NP / 16; ++k)
-              tc::mma_bf16_ts(tmem_base + h * NP + 128 + (k >> 2) * 32, tmem_base + h * NP + k * 8,
+              tc::mma_bf16_ts(tmem_base + h * NP + (k >> 2) * 64 + 32, tmem_base + h * NP + (k >> 2) * 64 + (k & 3) * 8,
                               tc::desc_advance(dv, k * 1024), idesc_o, (k & 3) ? 1u : 0u);
             tc::mma_commit(&o_full[h]);
             if (h == 1) tc::mma_commit(&qkv_empty[st]);
@@ -359,9 +359,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
         tc::tmem_ld_32x32b_x32(region + part * 64, x);
         tc::tmem_ld_32x32b_x32(region + part * 64 + 32, x + 32);
         tc::tmem_ld_wait();
-        // P of part 1 (this quadrant's other warp) lands on the upper half of part 0's logits and P of part 2 on
-        // part 1's: both loads of pass 0 must have completed before either warp stores
-        if (pass == 0) tc::named_bar_sync(1 + h * 4 + q4, 64);
+        // (P of a part goes back over the first 32 of its OWN 64 logit columns and its partial output accumulates
+        // in the other 32: no thread writes columns that another one still has to read)
         if (pass == 0) {
           if (ch == 0) add_bias<WD, WH, WW, 0>(x, bias_s, rowbase, cscale);
           else add_bias<WD, WH, WW, 1>(x, bias_s, rowbase, cscale);
@@ -391,7 +390,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
           x[k] = pack_bf16(p0, p1);
           x[k + 1] = pack_bf16(p2, p3);
         }
-        tc::tmem_st_32x32b_x32(region + part * 32, x);
+        tc::tmem_st_32x32b_x32(region + part * 64, x);
         stats[h * 512 + part * 128 + rl] = make_float2(m, l0 + l1);
         tc::mbar_arrive(&st_full[q4 * 2 + h]);
       }
@@ -410,7 +409,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
       const float inv = 1.f / l;
       tc::mbar_wait(&o_full[h], it & 1);
       tc::fence_after_sync();
-      const uint32_t ob = region + 128 + ch * 16;
+      const uint32_t ob = region + 32 + ch * 16;            // partial output of part p: columns 64 p + 32 ..
       float r[16];
       {
         uint32_t o[16];
@@ -418,15 +417,15 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
         tc::tmem_ld_wait();
 #pragma unroll
         for (int k = 0; k < 16; ++k) r[k] = w0 * __uint_as_float(o[k]);
-        tc::tmem_ld_32x32b_x16(ob + 32, o);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int k = 0; k < 16; ++k) r[k] = fmaf(w1, __uint_as_float(o[k]), r[k]);
         tc::tmem_ld_32x32b_x16(ob + 64, o);
         tc::tmem_ld_wait();
 #pragma unroll
+        for (int k = 0; k < 16; ++k) r[k] = fmaf(w1, __uint_as_float(o[k]), r[k]);
+        tc::tmem_ld_32x32b_x16(ob + 128, o);
+        tc::tmem_ld_wait();
+#pragma unroll
         for (int k = 0; k < 16; ++k) r[k] = fmaf(w2, __uint_as_float(o[k]), r[k]);
-        tc::tmem_ld_32x32b_x16(ob + 96, o);
+        tc::tmem_ld_32x32b_x16(ob + 192, o);
         tc::tmem_ld_wait();
 #pragma unroll
         for (int k = 0; k < 16; ++k) r[k] = fmaf(w3, __uint_as_float(o[k]), r[k]) * inv;
