@@ -9,9 +9,10 @@
 //          a 2-deep ring of {Q,K,V}[256][32] bf16 tiles in the 64-byte-swizzled UMMA layout (96 KB),
 //          per-token region codes and source rows of the window (written by the loader with the tiles).
 //   TMEM   two 256-column regions; region h holds S = Q_h K^T for the half h of the window's queries
-//          (128 lanes x 256 fp32 columns).  The softmax warps overwrite its first 128 columns with
-//          P (bf16 pairs) which feeds the second MMA from TMEM; the four partial outputs O_part = P_part V
-//          (one per 64-key part, each exponentiated against its own local max) sit in columns 128..255.
+//          (128 lanes x 256 fp32 columns = four 64-key parts).  A softmax thread writes P of a part (bf16
+//          pairs) back over the first 32 of the part's own 64 columns, from where it feeds the second MMA; the
+//          part's partial output O_part = P_part V (exponentiated against the part's local max) accumulates
+//          in the other 32 columns.
 //   warps  0-15 softmax in two independent groups (group = query half: its own TMEM region and barriers, so one
 //          group computes while the other waits for its MMAs), 16 = cp.async gather of the next window (roll and
 //          window_partition are index math on the source rows), 17 = MMA issuer (converged warp, elect.sync).
