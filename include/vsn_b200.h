@@ -94,6 +94,10 @@ int vsn_grid_copy(const float* src, int sD, int sH, int sW, float* dst, int dD, 
  * models/swin_transformer_3d.py:553-568.  x on the padded grid (pD,pH,pW), real extent (rD,rH,rW). */
 int vsn_merge_gather(float* x, int pD, int pH, int pW, int rD, int rH, int rW, float* out, int B, int C, int scatter,
                      void* stream);
+/* MixUp of fp16 volumes on the device (dataset/dataset.py:230-286, `sample1*alpha + sample2*(1-alpha)`):
+ * out[b] = lam[b]*x[b] + (1-lam[b])*x[perm[b]]; lam [B] fp32 (1 = sample left alone), perm [B] int32; not in place. */
+int vsn_mixup_f16(const void* x, void* out, const float* lam, const int* perm, int B, long long elems_per_sample,
+                  void* stream);
 int vsn_cast_rows_bf16(const float* src, void* dst, const float* row_scale, int rows_per_group, long long rows, int C,
                        void* stream);
 int vsn_cast_bf16(const float* src, void* dst, long long n, void* stream);

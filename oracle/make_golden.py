@@ -55,6 +55,39 @@ def grads_record(model, out):
             out[f"gfull/{k}"] = g.copy()
 
 
+def sample_index(key: str, numel: int, n: int = 256) -> np.ndarray:
+    """Fixed pseudo-random element positions of a parameter (same on every box: numpy MT19937 keyed on the name)."""
+    import zlib
+    rs = np.random.RandomState(zlib.crc32(("gsamp/" + key).encode()) & 0xFFFFFFFF)
+    return rs.randint(0, numel, size=min(n, numel)).astype(np.int64)
+
+
+def run_full_size_case(name, model, x, tgt, n_dp_calls):
+    """Train-mode forward + backward of the full-size model on the synthetic weights: logits, loss, and for EVERY
+    parameter the gradient norm, 256 sampled values (sample_index) and the whole tensor when it has <= 1024
+    elements.  This is what pins the backward of the real stage shapes (heads 3/6/12/24, 216..1 windows)."""
+    from regularization.label_smoothing import LabelSmoothingLoss
+    out = {}
+    model.train()
+    masks = synth_keep_masks(max(n_dp_calls, 1), x.shape[0], keep=0.7, seed=3)
+    refshim.DropPath.forced_masks = iter([torch.from_numpy(m) for m in masks])
+    model.zero_grad(set_to_none=True)
+    logits = model(x)
+    loss = LabelSmoothingLoss(smoothing=0.1)(logits, tgt)
+    loss.backward()
+    refshim.DropPath.forced_masks = None
+    out["logits_train"] = logits.detach().numpy()
+    out["loss"] = np.float64(loss.item())
+    for k, p in model.named_parameters():
+        g = p.grad.detach().numpy().astype(np.float32).reshape(-1)
+        out[f"gnorm/{k}"] = np.float64(np.sqrt((g.astype(np.float64) ** 2).sum()))
+        out[f"gsamp/{k}"] = g[sample_index(k, g.size)].copy()
+        if g.size <= 1024:
+            out[f"gfull/{k}"] = g.copy()
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(name, "logits_train", out["logits_train"].round(5).tolist(), "loss", out["loss"])
+
+
 def run_model_case(name, model, x, tgt, n_dp_calls, stage_modules, to_tokens):
     from regularization.label_smoothing import LabelSmoothingLoss
     out = {}
@@ -190,6 +223,28 @@ def main():
                                  ("pos_embedding", "cls_token", "to_patch_embedding.2.weight",
                                   "transformer.layers.11.1.net.4.weight", "mlp_head.1.weight")}
     meta["full"] = full
+
+    # ---- full-size TRAIN-mode gradients on the synthetic weights (B = 2, injected DropPath decisions) -----------
+    case = dict(SWIN_FULL, num_classes=5, drop_path=0.15, input=[2, 1, 144, 168, 144])
+    torch.manual_seed(0)
+    model = SwinTransformerT(**swin_ctor_kwargs(case))
+    load_synth(model)
+    x = torch.from_numpy(synth_volume(case["input"], seed=1))
+    tgt = torch.from_numpy(synth_targets(2, 5, seed=2))
+    run_full_size_case("swin5c_full_train", model, x, tgt, 2 * (sum(case["depths"]) - 1))
+    meta["swin5c_full_train"] = {"state_shapes": {k: list(v.shape) for k, v in model.state_dict().items()},
+                                 "param_order": [k for k, _ in model.named_parameters()]}
+    del model
+    vcase = dict(VIT_FULL, num_classes=3, input=[2, 1, 144, 160, 144])
+    torch.manual_seed(0)
+    model = ViTS(**vit_ctor_kwargs(vcase))
+    load_synth(model)
+    x = torch.from_numpy(synth_volume(vcase["input"], seed=1))
+    tgt = torch.from_numpy(synth_targets(2, 3, seed=2))
+    run_full_size_case("vit3c_full_train", model, x, tgt, 0)
+    meta["vit3c_full_train"] = {"state_shapes": {k: list(v.shape) for k, v in model.state_dict().items()},
+                                "param_order": [k for k, _ in model.named_parameters()]}
+    del model
     print("full", {k: v for k, v in full.items() if "seed0" in k})
 
     # ---- SAM / EMA trajectories on a tiny parameter set --------------------------------
@@ -215,6 +270,29 @@ def main():
             sam_out[f"final_{int(adaptive)}_{i}"] = p.detach().numpy().copy()
     for i, (p, g) in enumerate(zip(p0, g0)):
         sam_out[f"p0_{i}"], sam_out[f"g0_{i}"] = p, g
+    # non-finite and zero gradients (regularization/sam.py:46-52,66-70,141-153): "inf1" = one tensor holds an inf,
+    # "nan2" = another holds a nan, "allbad" = every tensor is non-finite, "zero" = all gradients are zero
+    def bad_grads(tag):
+        gs = [g.copy() for g in g0]
+        if tag == "inf1":
+            gs[1][3] = np.inf
+        elif tag == "nan2":
+            gs[2][0, 1, 2] = np.nan
+        elif tag == "allbad":
+            for g in gs:
+                g.reshape(-1)[0] = np.inf
+        elif tag == "zero":
+            gs = [np.zeros_like(g) for g in gs]
+        return gs
+    for tag in ("inf1", "nan2", "allbad", "zero"):
+        ps = [torch.nn.Parameter(torch.from_numpy(p.copy())) for p in p0]
+        opt = SAM([{"params": ps}], torch.optim.AdamW, rho=0.05, adaptive=False, lr=1e-3, weight_decay=0.05)
+        for p, g in zip(ps, bad_grads(tag)):
+            p.grad = torch.from_numpy(g)
+        sam_out[f"nf_{tag}_norm"] = np.float64(opt._grad_norm().item())
+        opt.first_step(zero_grad=False)
+        for i, p in enumerate(ps):
+            sam_out[f"nf_{tag}_pert_{i}"] = p.detach().numpy().copy()
     np.savez_compressed(os.path.join(GOLD, "sam.npz"), **sam_out)
 
     lin = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.BatchNorm1d(3))

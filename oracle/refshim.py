@@ -52,8 +52,8 @@ def _to_3tuple(x):
 
 def reference_root() -> str | None:
     here = os.path.dirname(os.path.abspath(__file__))
-    for cand in (os.environ.get("VSN_REFERENCE_ROOT"), "/root/reference",
-                 os.path.join(here, "..", "baseline", "_ref")):
+    for cand in (os.environ.get("VSN_REFERENCE_ROOT"), os.path.join(here, "..", "baseline", "_ref"),
+                 "/root/reference"):
         if cand and os.path.isdir(os.path.join(cand, "models")):
             return os.path.abspath(cand)
     return None

@@ -138,9 +138,10 @@ def test_vit3c_full_size_seed0_logits():
     assert rel_err(z, full["vit3c_seed0_in144x160x144"]) < TOL
 
 
-def test_in_kernel_gradient_accumulation_matches_autograd():
-    """TrainStep sums the block gradients of an optimiser step's micro-batches inside the kernels
-    (swin.GradAccumulation) and releases them to autograd once; same result as autograd's per-parameter adds."""
+def test_in_place_gradient_accumulation_matches_autograd():
+    """TrainStep lets the kernels accumulate the parameter gradients of an optimiser step's micro-batches straight
+    into the flat .grad arena (swin.GradSink); same result as autograd's per-parameter adds.  The CUDA-graph replay
+    of the micro-batch gives the same sums again."""
     swin_model, _ = _models()
     from vsn_b200 import swin
     from vsn_b200.train import TrainStep, soft_target_ce
@@ -149,27 +150,59 @@ def test_in_kernel_gradient_accumulation_matches_autograd():
     _load_synth(model, meta()["swin_small_even"]["state_shapes"])
     xs = [torch.from_numpy(synth_volume(case["input"], seed=10 + i)).cuda() for i in range(3)]
     ys = [torch.from_numpy(synth_targets(xs[0].shape[0], case["num_classes"], seed=20 + i)).cuda() for i in range(3)]
-    nblk = sum(case["depths"])
 
-    def run(in_kernel):
-        model.zero_grad(set_to_none=True)
-        masks = synth_keep_masks(3 * max(2 * (nblk - 1), 1), xs[0].shape[0], keep=0.7, seed=5)
-        swin_model.DropPath.forced_masks = iter(torch.from_numpy(mm) for mm in masks)
-        try:
-            if in_kernel:
-                ts = TrainStep(model, use_ema=False)
-                ts._accumulate(list(zip(xs, ys)))
-            else:
-                for x, y in zip(xs, ys):
-                    (soft_target_ce(model(x), y, 0.1) / 3).backward()
-        finally:
-            swin_model.DropPath.forced_masks = None
-        assert not swin.GradAccumulation.store and not swin.GradAccumulation.active
-        return {k: p.grad.clone() for k, p in model.named_parameters()}
+    model.zero_grad(set_to_none=True)
+    for x, y in zip(xs, ys):
+        (soft_target_ce(model(x), y, 0.1) / 3).backward()
+    ref = {k: p.grad.clone() for k, p in model.named_parameters()}
+    model.zero_grad(set_to_none=True)
 
-    ref, got = run(False), run(True)
-    for k in ref:
-        assert rel_err(got[k], ref[k]) < 1e-4, k
+    ts = TrainStep(model, use_ema=False)
+    ptrs = [p.grad.data_ptr() for p in model.parameters()]
+    loss = ts._accumulate(list(zip(xs, ys)))
+    assert not swin.GradSink.enabled and swin.GradSink.notify is None
+    assert ptrs == [p.grad.data_ptr() for p in model.parameters()]
+    for k, p in model.named_parameters():
+        assert rel_err(p.grad, ref[k]) < 1e-4, k
+    ts.grad_sync.zero_grad()
+    ts.grad_sync.remove()
+
+    tg = TrainStep(model, use_ema=False, graph=True)
+    for rep in range(2):                                  # capture + replay, then replay only
+        loss_g = tg._accumulate(list(zip(xs, ys)))
+        for k, p in model.named_parameters():
+            assert rel_err(p.grad, ref[k]) < 1e-4, (rep, k)
+        assert abs(float(loss_g) - float(loss)) < 1e-5 * abs(float(loss))
+        tg.grad_sync.zero_grad()
+    assert tg.graph_kernel_nodes > 50 and tg.graph_replays == 6
+    tg.grad_sync.remove()
+
+
+def test_train_step_graph_matches_eager_over_optimiser_steps():
+    """Three SAM(AdamW)+EMA optimiser steps with the micro-batch replayed from a CUDA graph end on the same weights
+    as the eager loop (DropPath off: the two runs would otherwise draw different keep masks)."""
+    swin_model, _ = _models()
+    from vsn_b200.train import TrainStep
+    case = SWIN_CASES["swin_small_even"]
+    xs = [torch.from_numpy(synth_volume(case["input"], seed=30 + i)).cuda() for i in range(2)]
+    ys = [torch.from_numpy(synth_targets(xs[0].shape[0], case["num_classes"], seed=40 + i)).cuda() for i in range(2)]
+    finals = []
+    for graph in (False, True):
+        model = swin_model.SwinTransformerT(**swin_ctor_kwargs(case)).cuda().train()
+        _load_synth(model, meta()["swin_small_even"]["state_shapes"])
+        ts = TrainStep(model, use_sam=True, use_ema=True, graph=graph, lr=1e-3)
+        losses = [float(ts.step(list(zip(xs, ys)))) for _ in range(3)]
+        finals.append(({k: p.detach().clone() for k, p in model.named_parameters()}, losses,
+                       {k: v.clone() for k, v in ts.ema.model_state.items()}))
+        ts.grad_sync.remove()
+    (pe, le, ee), (pg, lg, eg) = finals
+    assert le[2] < le[0]                                   # it trains
+    for a, b in zip(le, lg):
+        assert abs(a - b) < 2e-3 * abs(a), (le, lg)
+    for k in pe:
+        # Adam turns round-off-level differences of near-zero gradients (atomic summation order) into +-lr steps
+        assert rel_err(pg[k], pe[k]) < 1e-2, k
+        assert rel_err(eg[k], ee[k]) < 1e-2, k
 
 
 def test_droppath_factors_one_draw():
@@ -206,3 +239,62 @@ def test_droppath_factors_one_draw():
             assert sc.shape == (x.shape[0],) and sc.is_contiguous()
             ok = (sc == 0) | ((sc - 1.0 / (1.0 - q)).abs() < 1e-6)
             assert bool(ok.all())
+
+
+def _full_size_grad_check(model, g, x, tgt, masks, swin_model):
+    """Train-mode forward + backward at full size against the reference's golden: logits, loss, and for every
+    parameter the gradient norm, 256 sampled values and (small tensors) the whole gradient."""
+    from oracle.make_golden import sample_index
+    model.train()
+    swin_model.DropPath.forced_masks = iter(torch.from_numpy(mm) for mm in masks) if masks is not None else None
+    try:
+        logits = model(x)
+    finally:
+        swin_model.DropPath.forced_masks = None
+    loss = O.soft_target_ce(logits, tgt, 0.1)
+    loss.backward()
+    assert rel_err(logits.detach(), g["logits_train"]) < TOL
+    assert abs(loss.item() - float(g["loss"])) < TOL * abs(float(g["loss"]))
+    worst = ("", 0.0)
+    for k, p in model.named_parameters():
+        gr = p.grad.detach().float().reshape(-1)
+        n, want = float(gr.double().norm()), float(g[f"gnorm/{k}"])
+        assert abs(n - want) <= TOL * max(want, 1e-6), (k, n, want)
+        idx = torch.from_numpy(sample_index(k, gr.numel())).cuda()
+        e = rel_err(gr[idx], g[f"gsamp/{k}"])
+        if f"gfull/{k}" in g:
+            e = max(e, rel_err(gr, g[f"gfull/{k}"]))
+        if e > worst[1]:
+            worst = (k, e)
+    return worst
+
+
+def test_swin5c_full_size_train_gradients():
+    """swin-5c geometry at 144x168x144, B = 2, injected DropPath decisions: the backward of the real stage shapes
+    (216/27/8/1 windows per volume, heads 3/6/12/24, padded stages 2 and 3) against the unmodified reference."""
+    swin_model, _ = _models()
+    g, m = golden("swin5c_full_train"), meta()["swin5c_full_train"]
+    case = dict(SWIN_FULL, num_classes=5, drop_path=0.15, input=[2, 1, 144, 168, 144])
+    model = swin_model.SwinTransformerT(**swin_ctor_kwargs(case)).cuda()
+    assert [k for k, _ in model.named_parameters()] == m["param_order"]
+    _load_synth(model, m["state_shapes"])
+    x = torch.from_numpy(synth_volume(case["input"], seed=1)).cuda()
+    tgt = torch.from_numpy(synth_targets(2, 5, seed=2)).cuda()
+    masks = synth_keep_masks(2 * (sum(case["depths"]) - 1), 2, keep=0.7, seed=3)
+    worst = _full_size_grad_check(model, g, x, tgt, masks, swin_model)
+    print("WORST_GRAD swin5c_full_train", worst)
+    assert worst[1] < TOL, worst
+
+
+def test_vit3c_full_size_train_gradients():
+    swin_model, vit_model = _models()
+    g, m = golden("vit3c_full_train"), meta()["vit3c_full_train"]
+    case = dict(VIT_FULL, num_classes=3, input=[2, 1, 144, 160, 144])
+    model = vit_model.ViTS(**vit_ctor_kwargs(case)).cuda()
+    assert [k for k, _ in model.named_parameters()] == m["param_order"]
+    model.load_state_dict(synth_sd(m["state_shapes"], device="cuda"))
+    x = torch.from_numpy(synth_volume(case["input"], seed=1)).cuda()
+    tgt = torch.from_numpy(synth_targets(2, 3, seed=2)).cuda()
+    worst = _full_size_grad_check(model, g, x, tgt, None, swin_model)
+    print("WORST_GRAD vit3c_full_train", worst)
+    assert worst[1] < TOL, worst

@@ -124,3 +124,35 @@ def test_ema_oracle_matches_reference():
                 np.testing.assert_allclose(O.ema_average(states, 0.999), want, rtol=1e-6, atol=1e-7)
             else:
                 np.testing.assert_array_equal(states[-1], want)
+
+
+def test_product_index_buffer_and_seed0_init_bit_exact():
+    """The drop-in's `relative_position_index` buffer (state_dict payload) and its seed-0 initialisation are
+    bit-identical to the reference's (models/swin_transformer_3d.py:132-152,159,676-683): sha1 of the bytes against
+    the hashes the golden generator took from the unmodified reference.  Host-side only (no kernel runs)."""
+    import hashlib
+    import vsn_b200  # noqa: F401
+    from vsn_b200 import swin, swin_model, vit_model
+    from oracle.cases import SWIN_FULL, VIT_FULL, swin_ctor_kwargs, vit_ctor_kwargs
+
+    def sha16(a):
+        return hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+    kat, full = meta()["kat"], meta()["full"]
+    rpi = swin.relative_position_index((6, 7, 6)).numpy()
+    assert rpi.dtype == np.int64 and list(rpi.shape) == kat["rpi"]["shape"] and sha16(rpi) == kat["rpi"]["sha16"]
+    assert sha16(swin.relative_position_index((7, 7, 7)).numpy()) == kat["rpi_777"]["sha16"]
+    torch.manual_seed(0)
+    m5 = swin_model.SwinTransformerT(**swin_ctor_kwargs(dict(SWIN_FULL, num_classes=5, drop_path=0.15)))
+    sd = m5.state_dict()
+    assert len(sd) == full["swin5c_n_keys"] and sum(p.numel() for p in m5.parameters()) == full["swin5c_n_params"]
+    assert {k: list(v.shape) for k, v in sd.items()} == full["swin5c_state_shapes"]
+    for k, h in full["swin5c_param_sha16"].items():
+        assert sha16(sd[k].numpy()) == h, k
+    assert sha16(sd["backbone.layers.1.blocks.0.attn.relative_position_index"].numpy()) == kat["rpi"]["sha16"]
+    torch.manual_seed(0)
+    mv = vit_model.ViTS(**vit_ctor_kwargs(dict(VIT_FULL, num_classes=3)))
+    sdv = mv.state_dict()
+    assert {k: list(v.shape) for k, v in sdv.items()} == full["vit3c_state_shapes"]
+    for k, h in full["vit3c_param_sha16"].items():
+        assert sha16(sdv[k].numpy()) == h, k

@@ -15,13 +15,6 @@
 #include "common.cuh"
 #include "wattn_tc.cuh"
 
-// VSN_B200_LEGACY_ATTN=1 keeps the mma.sync kernels for window attention too (A/B measurements only).
-static bool vsn_force_legacy_attn() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("VSN_B200_LEGACY_ATTN"); v = (e != nullptr && e[0] == '1') ? 1 : 0; }
-  return v == 1;
-}
-
 namespace {
 
 constexpr int TQ = 64;        // rows owned by one CTA (4 warps x 16)
@@ -716,7 +709,7 @@ extern "C" int vsn_attn_fwd(const void* qkv, void* out, float* lse, int S, int N
   if (S == 0) return 0;
   dim3 grid(p.Npad / TQ, heads, S);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (win && wattn_tc_supported(p.wd, p.wh, p.ww, hd) && !vsn_force_legacy_attn()) return wattn_tc_fwd(to_tc_args(p), st);
+  if (win && wattn_tc_supported(p.wd, p.wh, p.ww, hd)) return wattn_tc_fwd(to_tc_args(p), st);
 #define VSN_FWD(HD, WIN)                                                            \
   {                                                                                 \
     const size_t sm = 5 * Smem<HD>::TILE + extra_bytes<HD>(p, WIN, false);          \
@@ -743,12 +736,12 @@ extern "C" int vsn_attn_bwd(const void* qkv, const void* out, const void* dout, 
   p.lse = const_cast<float*>(lse); p.delta = delta; p.dqkv = reinterpret_cast<bf16*>(dqkv);
   p.dbias_dense = dbias_dense;
   VSN_CHECK(table == nullptr || dtable != nullptr, "bias table given without its gradient buffer");
-  const bool tc_path = win && wattn_tc_supported(p.wd, p.wh, p.ww, hd) && !vsn_force_legacy_attn();
+  const bool tc_path = win && wattn_tc_supported(p.wd, p.wh, p.ww, hd);
   VSN_CHECK(table == nullptr || tc_path || dbias_dense != nullptr, "the mma.sync path needs the dense bias-gradient scratch");
   if (S == 0) return 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bf16* o = reinterpret_cast<const bf16*>(out);
-  if (win && wattn_tc_supported(p.wd, p.wh, p.ww, hd) && !vsn_force_legacy_attn()) {
+  if (win && wattn_tc_supported(p.wd, p.wh, p.ww, hd)) {
     p.out = const_cast<bf16*>(o);
     WinAttnArgs ta = to_tc_args(p);
     ta.dtable = table != nullptr ? dtable : nullptr;

@@ -50,7 +50,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-cudart", "static"]
+    # shared CUDA runtime (the process already holds torch's libcudart.so.12; /usr/local/cuda for stand-alone loads)
+    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

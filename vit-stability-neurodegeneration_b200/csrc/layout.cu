@@ -270,6 +270,34 @@ __global__ void vit_assemble_bwd_kernel(const float* __restrict__ dx, float* __r
   }
 }
 
+// MixUp of fp16 volumes (dataset/dataset.py:276-281: sample1 * alpha + sample2 * (1 - alpha)):
+// out[b] = lam[b] * x[b] + (1 - lam[b]) * x[perm[b]], fp32 arithmetic, 16-byte accesses.  lam[b] == 1 copies x[b].
+__global__ void mixup_f16_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, const float* __restrict__ lam,
+                                 const int* __restrict__ perm, int B, long long vec_per_sample) {
+  const long long total = static_cast<long long>(B) * vec_per_sample;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / vec_per_sample);
+    const long long r = i - static_cast<long long>(b) * vec_per_sample;
+    const float l = lam[b];
+    uint4 a = x[i];
+    if (l != 1.0f) {
+      const uint4 c = x[static_cast<long long>(perm[b]) * vec_per_sample + r];
+      const __half2* ah = reinterpret_cast<const __half2*>(&a);
+      const __half2* ch = reinterpret_cast<const __half2*>(&c);
+      uint4 o;
+      __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 fa = __half22float2(ah[k]), fc = __half22float2(ch[k]);
+        oh[k] = __floats2half2_rn(fmaf(l, fa.x, (1.0f - l) * fc.x), fmaf(l, fa.y, (1.0f - l) * fc.y));
+      }
+      a = o;
+    }
+    out[i] = a;
+  }
+}
+
 inline unsigned grid_for(long long total, int block) {
   long long g = ceil_div_ll(total, block);
   const long long cap = static_cast<long long>(vsn_num_sms()) * 16;
@@ -406,6 +434,20 @@ extern "C" int vsn_vit_assemble(const float* emb, const float* cls, const float*
 extern "C" int vsn_vit_assemble_bwd(const float* dx, float* dcls, float* dpos, int B, int T, int C, void* stream) {
   const long long total = static_cast<long long>(T + 1) * C;
   vit_assemble_bwd_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dx, dcls, dpos, B, T, C);
+  VSN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vsn_mixup_f16(const void* x, void* out, const float* lam, const int* perm, int B,
+                             long long elems_per_sample, void* stream) {
+  VSN_CHECK(elems_per_sample % 8 == 0, "vsn_mixup_f16: elements per sample must be a multiple of 8");
+  VSN_CHECK(reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0,
+            "vsn_mixup_f16: 16-byte aligned volumes expected");
+  VSN_CHECK(x != out, "vsn_mixup_f16: not in place (a sample is read as its own partner's input)");
+  const long long total = static_cast<long long>(B) * (elems_per_sample / 8);
+  if (total == 0) return 0;
+  mixup_f16_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), lam, perm, B, elems_per_sample / 8);
   VSN_LAUNCH_CHECK();
   return 0;
 }

@@ -95,6 +95,15 @@ __global__ void sam_scale_kernel(const float* sq, int n, float rho, float* out, 
   }
 }
 
+// The element-wise kernels below move 16 bytes per thread and access (float4; 8-byte bf16x4 stores in the cast), four
+// independent accesses in flight per array: one chunk is 64 KB per array, a block streams it in 16 float4 per thread.
+// Tensors (or tails) that are not 16-byte aligned / a multiple of 4 take the scalar loop.
+__device__ __forceinline__ bool aligned16(const void* a, const void* b = nullptr, const void* c = nullptr,
+                                          const void* d = nullptr, const void* e = nullptr) {
+  return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
+           reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(e)) & 15) == 0;
+}
+
 // old = p;  p += (p^2 if adaptive else 1) * g * scale   (skipped per tensor flag / when scale == 0)
 __global__ void __launch_bounds__(MT_THREADS) mt_sam_perturb_kernel(const long long* p_ptrs, const long long* g_ptrs,
                                                                     const long long* old_ptrs, MTTable tab,
@@ -106,7 +115,25 @@ __global__ void __launch_bounds__(MT_THREADS) mt_sam_perturb_kernel(const long l
   const float* g = reinterpret_cast<const float*>(g_ptrs[tensor]) + off;
   float* old = reinterpret_cast<float*>(old_ptrs[tensor]) + off;
   const float scale = skip_flags[tensor] ? 0.f : scale_dev[0];
-  for (long long i = threadIdx.x; i < n; i += MT_THREADS) {
+  long long done = 0;
+  if (aligned16(p, g, old)) {
+    const long long n4 = n >> 2;
+#pragma unroll 4
+    for (long long i = threadIdx.x; i < n4; i += MT_THREADS) {
+      float4 w = reinterpret_cast<float4*>(p)[i];
+      reinterpret_cast<float4*>(old)[i] = w;
+      if (scale != 0.f) {
+        const float4 gv = reinterpret_cast<const float4*>(g)[i];
+        w.x = w.x + (adaptive ? w.x * w.x : 1.0f) * gv.x * scale;
+        w.y = w.y + (adaptive ? w.y * w.y : 1.0f) * gv.y * scale;
+        w.z = w.z + (adaptive ? w.z * w.z : 1.0f) * gv.z * scale;
+        w.w = w.w + (adaptive ? w.w * w.w : 1.0f) * gv.w * scale;
+        reinterpret_cast<float4*>(p)[i] = w;
+      }
+    }
+    done = n4 << 2;
+  }
+  for (long long i = done + threadIdx.x; i < n; i += MT_THREADS) {
     const float w = p[i];
     old[i] = w;
     if (scale != 0.f) p[i] = w + (adaptive ? w * w : 1.0f) * g[i] * scale;
@@ -119,7 +146,15 @@ __global__ void __launch_bounds__(MT_THREADS) mt_copy_kernel(const long long* ds
   if (!chunk_span(tab, tensor, off, n)) return;
   float* d = reinterpret_cast<float*>(dst_ptrs[tensor]) + off;
   const float* s = reinterpret_cast<const float*>(src_ptrs[tensor]) + off;
-  for (long long i = threadIdx.x; i < n; i += MT_THREADS) d[i] = s[i];
+  long long done = 0;
+  if (aligned16(d, s)) {
+    const long long n4 = n >> 2;
+#pragma unroll 4
+    for (long long i = threadIdx.x; i < n4; i += MT_THREADS)
+      reinterpret_cast<float4*>(d)[i] = reinterpret_cast<const float4*>(s)[i];
+    done = n4 << 2;
+  }
+  for (long long i = done + threadIdx.x; i < n; i += MT_THREADS) d[i] = s[i];
 }
 
 // slot_new = p;  ema = w0*s0 + w1*s1 + w2*p accumulated oldest -> newest with fma (k = 1..3 live snapshots;
@@ -135,7 +170,28 @@ __global__ void __launch_bounds__(MT_THREADS) mt_ema_kernel(const long long* p_p
   const float* s0 = s0_ptrs ? reinterpret_cast<const float*>(s0_ptrs[tensor]) + off : nullptr;
   const float* s1 = s1_ptrs ? reinterpret_cast<const float*>(s1_ptrs[tensor]) + off : nullptr;
   float* ema = reinterpret_cast<float*>(ema_ptrs[tensor]) + off;
-  for (long long i = threadIdx.x; i < n; i += MT_THREADS) {
+  long long done = 0;
+  if (aligned16(p, snew, s0, s1, ema)) {
+    const long long n4 = n >> 2;
+#pragma unroll 4
+    for (long long i = threadIdx.x; i < n4; i += MT_THREADS) {
+      const float4 v = reinterpret_cast<const float4*>(p)[i];
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (s0) {
+        const float4 a = reinterpret_cast<const float4*>(s0)[i];
+        acc.x = fmaf(w0, a.x, acc.x); acc.y = fmaf(w0, a.y, acc.y); acc.z = fmaf(w0, a.z, acc.z); acc.w = fmaf(w0, a.w, acc.w);
+      }
+      if (s1) {
+        const float4 a = reinterpret_cast<const float4*>(s1)[i];
+        acc.x = fmaf(w1, a.x, acc.x); acc.y = fmaf(w1, a.y, acc.y); acc.z = fmaf(w1, a.z, acc.z); acc.w = fmaf(w1, a.w, acc.w);
+      }
+      acc.x = fmaf(w2, v.x, acc.x); acc.y = fmaf(w2, v.y, acc.y); acc.z = fmaf(w2, v.z, acc.z); acc.w = fmaf(w2, v.w, acc.w);
+      reinterpret_cast<float4*>(snew)[i] = v;
+      reinterpret_cast<float4*>(ema)[i] = acc;
+    }
+    done = n4 << 2;
+  }
+  for (long long i = done + threadIdx.x; i < n; i += MT_THREADS) {
     const float v = p[i];
     float acc = 0.f;
     if (s0) acc = fmaf(w0, s0[i], acc);
@@ -153,7 +209,17 @@ __global__ void __launch_bounds__(MT_THREADS) mt_cast_bf16_kernel(const long lon
   if (!chunk_span(tab, tensor, off, n)) return;
   const float* s = reinterpret_cast<const float*>(src_ptrs[tensor]) + off;
   bf16* d = reinterpret_cast<bf16*>(dst_ptrs[tensor]) + off;
-  for (long long i = threadIdx.x; i < n; i += MT_THREADS) d[i] = __float2bfloat16(s[i]);
+  long long done = 0;
+  if (aligned16(s) && (reinterpret_cast<uintptr_t>(d) & 7) == 0) {
+    const long long n4 = n >> 2;
+#pragma unroll 4
+    for (long long i = threadIdx.x; i < n4; i += MT_THREADS) {
+      const float4 v = reinterpret_cast<const float4*>(s)[i];
+      reinterpret_cast<uint2*>(d)[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    }
+    done = n4 << 2;
+  }
+  for (long long i = done + threadIdx.x; i < n; i += MT_THREADS) d[i] = __float2bfloat16(s[i]);
 }
 
 }  // namespace

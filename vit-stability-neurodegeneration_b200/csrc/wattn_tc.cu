@@ -27,7 +27,13 @@ constexpr int NP = 256;                    // padded tokens per window
 constexpr int HD = 32;
 constexpr int TILE_BYTES = NP * HD * 2;    // 16 KB
 constexpr int STAGE_BYTES = 3 * TILE_BYTES;   // Q | K | V (forward kernel; the one-hot region tile follows the ring)
-constexpr float REGION_ONE = 24.0f;          // one-hot value: REGION_ONE^2 * scale = 576 * 32^-1/2 = 101.8 nats, the reference's 100
+// One-hot region tiles of the forward's tensor-core shift mask: queries carry REGION_Q, keys REGION_K (both exact in
+// bf16).  REGION_Q * REGION_K * scale = 565.734375 * 32^-1/2 = 100.0087 nats: the reference's 100 to 9e-5 relative
+// (a single value e for both sides cannot do better than e^2 = 564.06 -> 99.7 or 576 -> 101.8 nats).
+constexpr float REGION_Q = 9.3125f;            // bf16 0x4115
+constexpr float REGION_K = 60.75f;             // bf16 0x4273
+constexpr uint32_t REGION_Q_BITS = 0x4115u, REGION_K_BITS = 0x4273u;
+constexpr float REGION_SQ = REGION_Q * REGION_K;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float MASK_L2E = -100.0f * LOG2E;
 constexpr float PAD_BIAS = -30000.0f;      // keys >= N
@@ -120,8 +126,8 @@ constexpr int FWD_STAGES = 2;
 
 template <int WD, int WH, int WW>
 struct FwdSmem {
-  static constexpr int ONEHOT = FWD_STAGES * STAGE_BYTES;      // one tile, shared by the two stages (see the loader)
-  static constexpr int BIAS = ONEHOT + TILE_BYTES;
+  static constexpr int ONEHOT = FWD_STAGES * STAGE_BYTES;      // query-side and key-side one-hot tiles, shared by the two stages (see the loader)
+  static constexpr int BIAS = ONEHOT + 2 * TILE_BYTES;
   static constexpr int KEYCODE = BIAS + BiasTab<WD, WH, WW>::BYTES;
   static constexpr int ROWIDX = KEYCODE + FWD_STAGES * NP;     // int [2][256] source row of every token + [2] masked flag
   static constexpr int STATS = ROWIDX + FWD_STAGES * NP * 4 + 16;   // float2 [2][4 parts][128]
@@ -212,7 +218,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
   if (warp == SM_WARPS + 1) tc::tmem_alloc(tmem_slot, 512);
   BT::build(p, head, bias_s);
   // rows N..255 of every tile stay zero for the whole kernel (the loader only writes rows < N)
-  for (int idx = threadIdx.x; idx < (FWD_STAGES * 3 + 1) * (NP - N) * 4; idx += blockDim.x) {
+  for (int idx = threadIdx.x; idx < (FWD_STAGES * 3 + 2) * (NP - N) * 4; idx += blockDim.x) {
     const int tile = idx / ((NP - N) * 4), rem = idx - tile * ((NP - N) * 4);
     const int row = N + rem / 4, c = rem & 3;
     *reinterpret_cast<uint4*>(stages + tile * TILE_BYTES + swz64(row, c)) = make_uint4(0, 0, 0, 0);
@@ -251,22 +257,27 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
         }
       }
       if (wc.masked()) {
-        // shift mask on the tensor cores: E[i][c] = REGION_ONE where c is the region of token i, so that
-        // (E E^T)[i][j] = REGION_ONE^2 for tokens of the same region, 0 otherwise -- added to Q K^T by two more K=16
-        // steps.  The reference adds -100 to pairs of DIFFERENT regions (models/swin_transformer_3d.py:463-492);
+        // shift mask on the tensor cores: Eq[i][c] = REGION_Q and Ek[i][c] = REGION_K where c is the region of token i,
+        // so that (Eq Ek^T)[i][j] = REGION_SQ for tokens of the same region, 0 otherwise -- added to Q K^T by two more
+        // K=16 steps.  The reference adds -100 to pairs of DIFFERENT regions (models/swin_transformer_3d.py:463-492);
         // softmax is invariant under the per-row constant that separates the two forms.
-        // The tile is not double-buffered: the S MMAs of the previous window (its second query half last) must have
-        // read it -- they retire while this window's Q / K / V are still in flight.
+        // The tiles are not double-buffered: the S MMAs of the previous window (its second query half last) must have
+        // read them -- they retire while this window's Q / K / V are still in flight.
         if (it > 0) tc::mbar_wait(&s_full[1], (it - 1) & 1);
         uint8_t* onehot = stages + FWD_STAGES * STAGE_BYTES;
         for (int i = lane; i < N; i += 32) {
           const int code = keycode[i];
-          uint32_t w[4] = {0u, 0u, 0u, 0u};
-          w[(code & 7) >> 1] = (code & 1) ? 0x41C00000u : 0x000041C0u;     // bf16 24.0 in the pair's high / low half
+          uint32_t wq[4] = {0u, 0u, 0u, 0u}, wk[4] = {0u, 0u, 0u, 0u};
+          wq[(code & 7) >> 1] = (code & 1) ? (REGION_Q_BITS << 16) : REGION_Q_BITS;   // the pair's high / low half
+          wk[(code & 7) >> 1] = (code & 1) ? (REGION_K_BITS << 16) : REGION_K_BITS;
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
+          for (int c = 0; c < 4; ++c) {
+            const bool hit = c == (code >> 3);
             *reinterpret_cast<uint4*>(onehot + swz64(i, c)) =
-                c == (code >> 3) ? make_uint4(w[0], w[1], w[2], w[3]) : make_uint4(0u, 0u, 0u, 0u);
+                hit ? make_uint4(wq[0], wq[1], wq[2], wq[3]) : make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(onehot + TILE_BYTES + swz64(i, c)) =
+                hit ? make_uint4(wk[0], wk[1], wk[2], wk[3]) : make_uint4(0u, 0u, 0u, 0u);
+          }
         }
       }
       if (lane == 0) winmask[st] = wc.masked() ? 1 : 0;
@@ -294,12 +305,12 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
             for (int k = 0; k < HD / 16; ++k)
               tc::mma_bf16_ss(tmem_base + h * NP, tc::desc_advance(dq, k * 32), tc::desc_advance(dk, k * 32), idesc_s,
                               k > 0 ? 1u : 0u);
-            if (win_masked) {        // + E_h E^T: the shift mask
+            if (win_masked) {        // + Eq_h Ek^T: the shift mask
               const uint64_t de = tc::desc_advance(desc_st0, FWD_STAGES * STAGE_BYTES);
 #pragma unroll
               for (int k = 0; k < 2; ++k)
                 tc::mma_bf16_ss(tmem_base + h * NP, tc::desc_advance(de, h * (128 * 64) + k * 32),
-                                tc::desc_advance(de, k * 32), idesc_s, 1u);
+                                tc::desc_advance(de, TILE_BYTES + k * 32), idesc_s, 1u);
             }
             tc::mma_commit(&s_full[h]);
           }
@@ -350,9 +361,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) wattn_fwd_kernel(const WinAttn
       tc::fence_after_sync();
       // geometry of the window as the loader worked it out (stage st is not refilled before this unit's P V ran)
       const int out_row = rowidx[st * NP + ib];
-      // masked windows carry REGION_ONE^2 * cscale on every same-region logit (the row maximum is one of them): taken
+      // masked windows carry REGION_SQ * cscale on every same-region logit (the row maximum is one of them): taken
       // out of the stored log-sum-exp, which the backward kernel combines with the reference's -100 form
-      const float lse_off = winmask[st] != 0 ? REGION_ONE * REGION_ONE * cscale : 0.f;
+      const float lse_off = winmask[st] != 0 ? REGION_SQ * cscale : 0.f;
 #pragma unroll
       for (int pass = 0; pass < 2; ++pass) {
         const int part = 2 * pass + ch;

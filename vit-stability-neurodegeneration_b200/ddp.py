@@ -5,13 +5,19 @@ Replaces what `torch.nn.parallel.DistributedDataParallel(...)` does for the refe
 over the ranks in ~25 MB buckets while backward is still running, and `model.no_sync()` skips the exchange on
 all but the last accumulation micro-batch, train/train_transformer.py:1131-1137,1225-1231).
 
-One process per GPU.  Gradients live in a few flat fp32 buckets; every parameter's `.grad` is a view into its
-bucket, so "packing" and "unpacking" cost nothing.  Buckets are laid out in reverse registration order, which
-is the order backward produces gradients (head + stage 3 first, patch embedding last); when the
-last gradient of a bucket has been accumulated a single `all_reduce(SUM)` of the whole bucket is enqueued on a
-communication stream (NCCL over NVLink / NVSwitch), overlapping the rest of backward; `finish()` makes the
-compute stream wait for the outstanding reductions and applies the 1/world mean.  There is no data-path
-collective anywhere else: volumes are independent units and the weights are replicated.
+One process per GPU.  All gradients live in ONE flat fp32 arena cut into buckets; every parameter's `.grad` is a
+view into its bucket, so "packing" and "unpacking" cost nothing and `zero_grad()` is a single fill.  Buckets are
+laid out in reverse registration order, which is the order backward produces gradients (head + stage 3 first,
+patch embedding last); when the last gradient of a bucket is complete a single `all_reduce(AVG)`
+of the whole bucket is enqueued on a communication stream (NCCL over NVLink / NVSwitch), overlapping the rest of
+backward; `finish()` makes the compute stream wait for the outstanding reductions.  At construction rank 0's
+parameters (and the buffers handed in) are broadcast, as DistributedDataParallel does, so replicas that were
+initialised differently cannot silently train different weights.  There is no data-path collective anywhere
+else: volumes are independent units and the weights are replicated.
+
+Gradients reach the arena in one of two ways: through autograd (`post_accumulate_grad` hooks count a bucket's
+parameters down), or written in place by the kernels (`swin.GradSink`, used by `train.TrainStep`), in which
+case the producer calls `mark_ready(grad)` itself.
 
 The same host logic runs on CPU tensors over the `gloo` backend (tests/test_ddp_cpu.py, world size 2).
 """
@@ -45,7 +51,7 @@ def plan_buckets(sizes: Sequence[int], cap_elems: int) -> List[List[int]]:
 class GradAllReduce:
     """Bucketed mean all-reduce of the gradients of `params`, overlapped with backward.
 
-        ddp = GradAllReduce(model.parameters())          # after the process group exists
+        ddp = GradAllReduce(model.parameters(), buffers=model.buffers())   # after the process group exists
         for micro in micro_batches[:-1]:
             with ddp.no_sync():
                 loss(micro).backward()                    # accumulate locally
@@ -53,73 +59,101 @@ class GradAllReduce:
         ddp.finish()                                      # grads are now the cross-rank mean
         optimizer.step(); ddp.zero_grad()
 
-    `.grad` of every parameter is a persistent view into a flat bucket: use `ddp.zero_grad()` (or
-    `optimizer.zero_grad(set_to_none=False)`), never `set_to_none=True`.
+    `.grad` of every parameter is a persistent view into the flat arena: use `ddp.zero_grad()` (or
+    `optimizer.zero_grad(set_to_none=False)`), never `set_to_none=True`.  With world size 1 (or no process group)
+    the object is just that arena: nothing is exchanged.
     """
 
     def __init__(self, params: Iterable[torch.nn.Parameter], bucket_mb: float = 25.0,
-                 group: Optional[dist.ProcessGroup] = None):
+                 group: Optional[dist.ProcessGroup] = None, buffers: Optional[Iterable[torch.Tensor]] = None,
+                 broadcast: bool = True):
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("GradAllReduce needs at least one parameter that requires grad")
         self.group = group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         dev = self.params[0].device
         for p in self.params:
             if p.device != dev or p.dtype != torch.float32:
                 raise RuntimeError("GradAllReduce expects fp32 parameters on one device")
         self.device = dev
+        if self.world > 1 and broadcast:
+            # DistributedDataParallel semantics: every replica starts from rank 0's state
+            src = dist.get_global_rank(group, 0) if group is not None else 0
+            for t in [p.data for p in self.params] + [b for b in (buffers or [])]:
+                dist.broadcast(t, src=src, group=group)
         cap = max(1, int(bucket_mb * 1024 * 1024 / 4))
         self.plan = plan_buckets([p.numel() for p in self.params], cap)
-        self.buckets: List[torch.Tensor] = []
-        self._bucket_of = {}
-        self._pending_init: List[int] = []
-        for b, idxs in enumerate(self.plan):
-            # 16-byte aligned slices so vectorised kernels can run on the views
-            offs, tot = [], 0
+        # one arena, buckets are consecutive slices of it; 16-byte aligned parameter slices so vectorised
+        # kernels can run on the views
+        layout, tot = [], 0
+        for idxs in self.plan:
+            start, offs = tot, []
             for i in idxs:
                 offs.append(tot)
                 tot += (self.params[i].numel() + 3) // 4 * 4
-            flat = torch.zeros(tot, device=dev, dtype=torch.float32)
-            self.buckets.append(flat)
+            layout.append((start, tot, offs))
+        self.arena = torch.zeros(tot, device=dev, dtype=torch.float32)
+        self.buckets: List[torch.Tensor] = []
+        self._bucket_of = {}
+        self._index_of_grad = {}
+        self._pending_init: List[int] = []
+        for b, (idxs, (start, end, offs)) in enumerate(zip(self.plan, layout)):
+            self.buckets.append(self.arena[start:end])
             for i, o in zip(idxs, offs):
                 p = self.params[i]
-                p.grad = flat[o: o + p.numel()].view_as(p)
+                p.grad = self.arena[o: o + p.numel()].view_as(p)
                 self._bucket_of[i] = b
+                self._index_of_grad[p.grad.data_ptr()] = i
             self._pending_init.append(len(idxs))
         self._pending = list(self._pending_init)
+        self._launched = [False] * len(self.buckets)
         self._sync = True
         self._works = []
         self._comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
-        self._events = []
         self._hooks = [p.register_post_accumulate_grad_hook(self._make_hook(i)) for i, p in enumerate(self.params)]
 
-    # ------------------------------------------------------------------ hooks
+    # ------------------------------------------------------------------ gradient arrival
     def _make_hook(self, i: int):
         def hook(param: torch.nn.Parameter):
-            b = self._bucket_of[i]
-            flat = self.buckets[b]
             g = param.grad
-            if g is None or g.untyped_storage().data_ptr() != flat.untyped_storage().data_ptr():
+            if g is None or g.untyped_storage().data_ptr() != self.arena.untyped_storage().data_ptr():
                 raise RuntimeError("a .grad was replaced (zero_grad(set_to_none=True)?): use GradAllReduce.zero_grad()")
-            if not self._sync or self.world == 1:
-                return
-            self._pending[b] -= 1
-            if self._pending[b] == 0:
-                self._launch(b)
+            self._arrived(i)
         return hook
+
+    def mark_ready(self, grad: torch.Tensor) -> None:
+        """The kernels have finished accumulating into this `.grad` view (enqueued on the current stream)."""
+        i = self._index_of_grad.get(grad.data_ptr())
+        if i is None:
+            raise RuntimeError("mark_ready: not a gradient view of this arena")
+        self._arrived(i)
+
+    def _arrived(self, i: int) -> None:
+        if not self._sync or self.world == 1:
+            return
+        b = self._bucket_of[i]
+        if self._launched[b]:
+            raise RuntimeError(
+                "a gradient arrived after its bucket was reduced: two synchronised backward passes without "
+                "finish() in between (or a parameter used twice); run the earlier passes under no_sync()")
+        self._pending[b] -= 1
+        if self._pending[b] == 0:
+            self._launch(b)
 
     def _launch(self, b: int) -> None:
         flat = self.buckets[b]
+        self._launched[b] = True
+        op = dist.ReduceOp.AVG if self.device.type == "cuda" else dist.ReduceOp.SUM
         if self._comm_stream is not None:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(self.device))       # the bucket's gradients are complete here
             self._comm_stream.wait_event(ev)
             with torch.cuda.stream(self._comm_stream):
-                work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                work = dist.all_reduce(flat, op=op, group=self.group, async_op=True)
             self._works.append(work)
         else:
-            self._works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            self._works.append(dist.all_reduce(flat, op=op, group=self.group, async_op=True))
 
     # ------------------------------------------------------------------ API
     @contextmanager
@@ -131,26 +165,31 @@ class GradAllReduce:
         finally:
             self._sync = old
 
-    def finish(self) -> None:
-        """Wait for the outstanding reductions and turn the sums into means.  Call after the last backward."""
+    def reduce_all(self) -> None:
+        """Reduce every bucket that has not been reduced yet, in bucket order (the same on every rank).  Used when
+        the producer gives no per-gradient notice (a captured CUDA graph) and for parameters that took no part."""
         if self.world > 1:
-            # buckets whose hooks did not all fire (unused parameters) are reduced now
-            for b, left in enumerate(self._pending):
-                if left != 0:
+            for b in range(len(self.buckets)):
+                if not self._launched[b]:
                     self._launch(b)
+
+    def finish(self) -> None:
+        """Wait for the outstanding reductions: gradients are the cross-rank mean afterwards.  Call after the last
+        backward.  Buckets some of whose parameters produced no gradient are reduced here, in fixed bucket order."""
+        if self.world > 1:
+            self.reduce_all()
             for w in self._works:
                 w.wait()            # NCCL: makes the current stream wait for the collective
             if self._comm_stream is not None:
                 torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
-            inv = 1.0 / self.world
-            for flat in self.buckets:
-                flat.mul_(inv)
+            else:                   # gloo has no AVG: sum, then scale
+                self.arena.mul_(1.0 / self.world)
         self._works = []
         self._pending = list(self._pending_init)
+        self._launched = [False] * len(self.buckets)
 
     def zero_grad(self) -> None:
-        for flat in self.buckets:
-            flat.zero_()
+        self.arena.zero_()
 
     def remove(self) -> None:
         for h in self._hooks:
@@ -159,4 +198,4 @@ class GradAllReduce:
 
     @property
     def bytes_per_reduce(self) -> int:
-        return sum(b.numel() for b in self.buckets) * 4
+        return self.arena.numel() * 4

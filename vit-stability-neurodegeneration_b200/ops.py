@@ -210,6 +210,9 @@ def patch_gather(vol: torch.Tensor, patch: Sequence[int], *, out_dtype=BF16) -> 
     pd, ph, pw = patch
     gd, gh, gw = -(-D // pd), -(-H // ph), -(-W // pw)
     out = torch.empty((B * gd * gh * gw, pd * ph * pw), device=vol.device, dtype=out_dtype)
+    if _lib.PROFILE is not None:
+        _lib.TAG = f"B{B} vol{D}x{H}x{W} patch{pd}x{ph}x{pw} in={vol.dtype} out={'bf16' if out_dtype == BF16 else 'f32'}"
+        _lib.WORK = (0, vol.numel() * vol.element_size() + out.numel() * out.element_size())
     _lib.call("vsn_patch_gather", _p(vol), _IN_DTYPE[vol.dtype], _p(out), 1 if out_dtype == BF16 else 0, B, D, H, W,
               pd, ph, pw, _stream())
     return out
@@ -217,6 +220,10 @@ def patch_gather(vol: torch.Tensor, patch: Sequence[int], *, out_dtype=BF16) -> 
 
 def grid_copy(src: torch.Tensor, sdims, ddims, B: int, C: int) -> torch.Tensor:
     dst = torch.empty((B * ddims[0] * ddims[1] * ddims[2], C), device=src.device, dtype=F32)
+    if _lib.PROFILE is not None:
+        overlap = B * C * min(sdims[0], ddims[0]) * min(sdims[1], ddims[1]) * min(sdims[2], ddims[2])
+        _lib.TAG = f"B{B} C{C} {tuple(sdims)}->{tuple(ddims)}"
+        _lib.WORK = (0, 4 * (overlap + dst.numel()))
     _lib.call("vsn_grid_copy", _p(src), *sdims, _p(dst), *ddims, B, C, _stream())
     return dst
 
@@ -224,14 +231,34 @@ def grid_copy(src: torch.Tensor, sdims, ddims, B: int, C: int) -> torch.Tensor:
 def merge_gather(x: torch.Tensor, pdims, rdims, B: int, C: int) -> torch.Tensor:
     od = [(r + 1) // 2 for r in rdims]
     out = torch.empty((B * od[0] * od[1] * od[2], 8 * C), device=x.device, dtype=F32)
+    if _lib.PROFILE is not None:
+        _lib.TAG = f"B{B} C{C} real{tuple(rdims)} gather"
+        _lib.WORK = (0, 4 * (B * C * rdims[0] * rdims[1] * rdims[2] + out.numel()))
     _lib.call("vsn_merge_gather", _p(x), *pdims, *rdims, _p(out), B, C, 0, _stream())
     return out
 
 
 def merge_scatter(dout: torch.Tensor, pdims, rdims, B: int, C: int) -> torch.Tensor:
     dx = torch.zeros((B * pdims[0] * pdims[1] * pdims[2], C), device=dout.device, dtype=F32)
+    if _lib.PROFILE is not None:
+        _lib.TAG = f"B{B} C{C} real{tuple(rdims)} scatter"
+        _lib.WORK = (0, 4 * (B * C * rdims[0] * rdims[1] * rdims[2] + dout.numel()))
     _lib.call("vsn_merge_gather", _p(dx), *pdims, *rdims, _p(dout), B, C, 1, _stream())
     return dx
+
+
+def mixup(x: torch.Tensor, lam: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
+    """out[b] = lam[b] * x[b] + (1 - lam[b]) * x[perm[b]] on fp16 volumes [B,1,D,H,W] (dataset/dataset.py:276-281)."""
+    assert x.dtype == torch.float16 and x.is_contiguous() and lam.dtype == F32 and perm.dtype == torch.int32
+    _require_cuda(x, lam, perm)
+    B = x.shape[0]
+    per = x.numel() // B
+    out = torch.empty_like(x)
+    if _lib.PROFILE is not None:
+        _lib.TAG = f"B{B} elems{per}"
+        _lib.WORK = (0, x.numel() * 6)
+    _lib.call("vsn_mixup_f16", _p(x), _p(out), _p(lam), _p(perm), B, per, _stream())
+    return out
 
 
 def cast_rows_bf16(src: torch.Tensor, row_scale=None, rows_per_group=1) -> torch.Tensor:

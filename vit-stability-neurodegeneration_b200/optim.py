@@ -74,21 +74,33 @@ class MultiTensorTable:
     def _stream():
         return torch.cuda.current_stream().cuda_stream
 
+    def _work(self, arrays: int, elem_bytes: float = 4.0) -> None:
+        """Algorithmic bytes of the next launch (bench.py's instrumented pass): `arrays` passes over all elements."""
+        if _lib.PROFILE is not None:
+            tot = sum(self.sizes_host)
+            _lib.TAG = f"tensors{self.n} elems{tot}"
+            _lib.WORK = (0, int(tot * elem_bytes * arrays))
+
     def sqnorm(self, g_ptrs, p_ptrs, sq, adaptive):
+        self._work(2 if adaptive else 1)
         _lib.call("vsn_mt_sqnorm", g_ptrs.data_ptr(), p_ptrs.data_ptr() if p_ptrs is not None else None, *self._tab(),
                   sq.data_ptr(), int(adaptive), self._stream())
 
     def sam_perturb(self, p_ptrs, g_ptrs, old_ptrs, scale, flags, adaptive):
+        self._work(4)                    # read p, g; write old_p, p  (16 B per parameter, SURVEY.md §8d)
         _lib.call("vsn_mt_sam_perturb", p_ptrs.data_ptr(), g_ptrs.data_ptr(), old_ptrs.data_ptr(), *self._tab(),
                   scale.data_ptr(), flags.data_ptr(), int(adaptive), self._stream())
 
     def copy(self, dst_ptrs, src_ptrs):
+        self._work(2)
         _lib.call("vsn_mt_copy", dst_ptrs.data_ptr(), src_ptrs.data_ptr(), *self._tab(), self._stream())
 
     def cast_bf16(self, src_ptrs, dst_ptrs):
+        self._work(1, 6.0)               # read fp32, write bf16
         _lib.call("vsn_mt_cast_bf16", src_ptrs.data_ptr(), dst_ptrs.data_ptr(), *self._tab(), self._stream())
 
     def ema(self, p_ptrs, new_ptrs, s0_ptrs, s1_ptrs, ema_ptrs, w0, w1, w2):
+        self._work(3 + (s0_ptrs is not None) + (s1_ptrs is not None))   # read p (+s0, s1); write the new slot and the average
         _lib.call("vsn_mt_ema", p_ptrs.data_ptr(), new_ptrs.data_ptr(),
                   s0_ptrs.data_ptr() if s0_ptrs is not None else None,
                   s1_ptrs.data_ptr() if s1_ptrs is not None else None, ema_ptrs.data_ptr(), *self._tab(),
@@ -126,7 +138,10 @@ class SAM(torch.optim.Optimizer):
         return ps
 
     def _get_plan(self, ps: List[torch.nn.Parameter]):
-        key = tuple((p.data_ptr(), p.numel()) for p in ps)
+        # the key covers the saved-weights tensors too: if optimizer.state was replaced (load_state_dict, a cleared
+        # state) the cached addresses would point at freed memory
+        key = tuple((p.data_ptr(), p.numel(), self.state[p]["old_p"].data_ptr() if "old_p" in self.state[p] else 0)
+                    for p in ps)
         if key != self._plan_key:
             for p in ps:
                 if p.dtype != F32 or not p.is_cuda:
@@ -138,10 +153,14 @@ class SAM(torch.optim.Optimizer):
             olds = []
             for p in ps:
                 st = self.state[p]
-                if "old_p" not in st or st["old_p"].shape != p.shape or st["old_p"].device != p.device:
+                o = st.get("old_p")
+                if (o is None or o.shape != p.shape or o.device != p.device or o.dtype != F32
+                        or not o.is_contiguous()):
                     st["old_p"] = torch.empty_like(p.detach(), memory_format=torch.contiguous_format)
                 olds.append(st["old_p"])
+            key = tuple((p.data_ptr(), p.numel(), o.data_ptr()) for p, o in zip(ps, olds))
             self._plan = dict(tab=tab, p=tab.ptr_array([p.detach() for p in ps]), old=tab.ptr_array(olds),
+                              olds=olds,           # referenced here so the addresses in `old` stay valid
                               gkey=None, g=None,
                               sq=torch.zeros(len(ps), device=dev, dtype=F32),
                               flags=torch.zeros(len(ps), device=dev, dtype=torch.int32),
@@ -212,6 +231,7 @@ class SAM(torch.optim.Optimizer):
     def load_state_dict(self, state_dict: Dict[str, Any]) -> None:
         super().load_state_dict(state_dict)
         self.base_optimizer.param_groups = self.param_groups
+        self._plan_key, self._plan = None, None     # state (old_p) was replaced: rebuild the pointer tables
 
 
 class EMAModel:

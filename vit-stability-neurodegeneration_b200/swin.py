@@ -17,6 +17,10 @@ from . import ops
 
 F32, BF16 = torch.float32, torch.bfloat16
 
+# dtype of the two activation gradients that feed the LayerNorm backward kernels (outputs of the qkv / fc1 dgrad GEMMs).
+# fp32 keeps the LayerNorm parameter gradients and the residual-stream gradient free of one bf16 rounding.
+LN_DY_DTYPE = BF16
+
 
 def _contig_f32(t: torch.Tensor) -> torch.Tensor:
     if t.dtype != F32:
@@ -40,12 +44,13 @@ class WeightShadow:
         self._flat = None
         self._views: List[torch.Tensor] = []
         self._table = None
+        self.hold = False       # True: forward() does not refresh (the caller does, once per optimiser pass)
 
-    def refresh(self) -> None:
+    def refresh(self, force: bool = False) -> None:
         from .optim import MultiTensorTable
         key = tuple((p.data_ptr(), p.numel()) for p in self.params)
-        if key == self._key and GradAccumulation.active and not GradAccumulation.first:
-            return      # a later micro-batch of the same optimiser step: the masters have not been written since
+        if key == self._key and self.hold and not force:
+            return      # the owner (train.TrainStep) refreshes once per optimiser pass: masters unchanged since
         if key != self._key:
             dev = self.params[0].device
             sizes = [(p.numel() + 7) // 8 * 8 for p in self.params]   # keep every view 16-byte aligned
@@ -65,34 +70,42 @@ class WeightShadow:
 
 
 # --------------------------------------------------------------------------------------
-# gradient accumulation over micro-batches inside the kernels
+# parameter gradients written in place by the kernels
 # --------------------------------------------------------------------------------------
-class GradAccumulation:
-    """Every parameter-gradient kernel of the path accumulates (+=).  Inside `with GradAccumulation.over(n)` the
-    block Functions keep ONE set of gradient buffers per block for all the micro-batches of an optimiser step and
-    hand them to autograd only on the last one: the non-final backward passes return no parameter gradients, so
-    autograd launches no per-parameter `grad += new` kernels, and the data-parallel hooks fire exactly once, when
-    the sums are complete (the same moment `DistributedDataParallel.no_sync()` would release them,
-    train/train_transformer.py:1131-1137).  Outside the context every backward returns its gradients as usual."""
+class GradSink:
+    """Every parameter-gradient kernel of the path accumulates (+=).  While the sink is enabled
+    (`train.TrainStep` does that) the Functions below accumulate straight into the parameters' persistent `.grad`
+    storage (views into the flat arena of `ddp.GradAllReduce`) and return no parameter gradients to autograd: no
+    per-block zero fills, no per-parameter `grad += new` kernels, and the micro-batches of an optimiser step sum up
+    in place -- the accumulation the reference gets from `loss.backward()` under `model.no_sync()`
+    (train/train_transformer.py:1131-1137).  `notify`, if set, is told which gradients a unit has just completed
+    (the data-parallel exchange reduces a bucket as soon as its last gradient is in).  Disabled, every backward
+    returns its gradients to autograd as usual (the reference trainer, torch DDP, `w.watch` hooks)."""
 
-    active = False
-    final = True
-    first = True        # first micro-batch of the optimiser step (later ones see unchanged weights)
-    store: dict = {}
-
-    @classmethod
-    def begin(cls, final: bool, first: bool = True) -> None:
-        cls.active, cls.final, cls.first = True, final, first
+    enabled = False
+    notify = None       # callable(list of .grad views) or None
 
     @classmethod
-    def end(cls) -> None:
-        cls.active, cls.final, cls.first = False, True, True
-        if not cls.store:
-            return
-        left = len(cls.store)
-        cls.store.clear()
-        raise RuntimeError(f"GradAccumulation: {left} blocks were left with unreleased gradients "
-                           "(the last micro-batch must run with final=True)")
+    def destinations(cls, *params):
+        """Called in forward: the `.grad` views the unit's backward will accumulate into, or None."""
+        if not cls.enabled:
+            return None
+        out = []
+        for p in params:
+            if p is None:
+                out.append(None)
+                continue
+            g = p.grad
+            if g is None or g.dtype != F32 or not g.is_contiguous() or g.shape != p.shape:
+                raise RuntimeError("GradSink needs a persistent contiguous fp32 .grad on every parameter "
+                                   "(ddp.GradAllReduce provides them)")
+            out.append(g)
+        return out
+
+    @classmethod
+    def done(cls, grads) -> None:
+        if cls.notify is not None:
+            cls.notify([g for g in grads if g is not None])
 
 
 # --------------------------------------------------------------------------------------
@@ -109,7 +122,6 @@ class BlockCfg:
     w16: Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor] = None   # qkv, proj, fc1, fc2 (bf16)
     scale1: Optional[torch.Tensor] = None   # DropPath keep/(1-p) per sample for the attention branch
     scale2: Optional[torch.Tensor] = None   # ... for the MLP branch
-    acc_key: int = 0                        # identity of the block (key of its GradAccumulation buffers)
     # backward side channel: the block that consumes this block's input gradient (the previous block of the stage)
     # starts by casting it to bf16 scaled by ITS MLP DropPath factor; when `emit_for_prev` is set this block's last
     # LayerNorm-backward kernel writes that bf16 copy as a second output and `take_from_next` tells the consumer to
@@ -145,6 +157,8 @@ class SwinBlockFn(torch.autograd.Function):
         ctx.cfg = cfg
         ctx.has_qkv_bias = qkv_b is not None
         ctx.has_table = table is not None
+        ctx.sink = GradSink.destinations(qkv_w, proj_w, fc1_w, fc2_w, qkv_b, proj_b, fc1_b, fc2_b, n1w, n1b, n2w, n2b,
+                                         table)
         ctx.save_for_backward(x, mean1, rstd1, y1, qkv, o, lse, x1, mean2, rstd2, y2, h, a, n1w, n2w,
                               table if table is not None else n1w)
         ctx.shapes = (qkv_w.shape, proj_w.shape, fc1_w.shape, fc2_w.shape)
@@ -162,20 +176,20 @@ class SwinBlockFn(torch.autograd.Function):
         dev = x.device
         C = x.shape[1]
         g = _contig_f32(g)
-        # all parameter-gradient accumulators of the block come from ONE zero-filled buffer (one fill kernel
-        # instead of 13); every kernel below accumulates (+=) into its slice
-        shapes = [*ctx.shapes, (ctx.shapes[0][0],), (C,), (w1.shape[0],), (C,), (C,), (C,), (C,), (C,)]
-        if table is not None:
-            shapes.append(tuple(table.shape))
-        acc = GradAccumulation
-        bufs = acc.store.get(cfg.acc_key) if acc.active else None
-        if bufs is None:
+        if ctx.sink is not None:
+            # in-place mode: the kernels accumulate into the parameters' own .grad storage
+            bufs = [b.view(-1) if b is not None and b.dim() == 0 else b for b in ctx.sink]
+            if not ctx.has_qkv_bias:
+                bufs[4] = None
+            release = False
+        else:
+            # all parameter-gradient accumulators of the block come from ONE zero-filled buffer (one fill kernel
+            # instead of 13); every kernel below accumulates (+=) into its slice
+            shapes = [*ctx.shapes, (ctx.shapes[0][0],), (C,), (w1.shape[0],), (C,), (C,), (C,), (C,), (C,)]
+            if table is not None:
+                shapes.append(tuple(table.shape))
             bufs = zeros_like_shapes(shapes, dev)
-            if acc.active and not acc.final:
-                acc.store[cfg.acc_key] = bufs
-        elif acc.final:
-            del acc.store[cfg.acc_key]
-        release = not acc.active or acc.final            # hand the gradients to autograd in this pass?
+            release = True
         (d_qkv_w, d_proj_w, d_fc1_w, d_fc2_w, d_qkv_b, d_proj_b, d_fc1_b, d_fc2_b, d_n1w, d_n1b, d_n2w, d_n2b,
          *rest) = bufs
         d_table = rest[0] if table is not None else None
@@ -186,7 +200,7 @@ class SwinBlockFn(torch.autograd.Function):
         ops.linear_wgrad(gs, a, d_fc2_w, dbias=d_fc2_b)
         dh = ops.linear_dgrad(gs, w2, gelu_aux=h)
         ops.linear_wgrad(dh, y2, d_fc1_w, dbias=d_fc1_b)
-        dy2 = ops.linear_dgrad(dh, w1)
+        dy2 = ops.linear_dgrad(dh, w1, out_dtype=LN_DY_DTYPE)
         g1, g1s = ops.layernorm_bwd(dy2, x1, mean2, rstd2, n2w, resid_grad=g, want_bf16=True, row_scale=cfg.scale1,
                                     rows_per_group=tps, dgamma=d_n2w, dbeta=d_n2b)
         # ---- attention branch: x1 = x + s1 * (Wp attn(Wq LN1(x) + bq) + bp)
@@ -195,13 +209,14 @@ class SwinBlockFn(torch.autograd.Function):
         dqkv = ops.attn_bwd(qkv, o, do, lse, cfg.heads, cfg.hd, S=S, N=N, scale=cfg.hd ** -0.5, geom=geom,
                             table=table, dtable=d_table)
         ops.linear_wgrad(dqkv, y1, d_qkv_w, dbias=d_qkv_b if ctx.has_qkv_bias else None)
-        dy1 = ops.linear_dgrad(dqkv, wq)
+        dy1 = ops.linear_dgrad(dqkv, wq, out_dtype=LN_DY_DTYPE)
         g0, g0b = ops.layernorm_bwd(dy1, x, mean1, rstd1, n1w, resid_grad=g1, dx_out=g1, dgamma=d_n1w, dbeta=d_n1b,
                                     want_bf16=cfg.emit_for_prev, row_scale=cfg.prev_scale2, rows_per_group=tps)
         if cfg.emit_for_prev:
             _SIDE.clear()                       # at most one pending hand-over
             _SIDE[g0.data_ptr()] = g0b
         if not release:
+            GradSink.done(ctx.sink)
             return (g0,) + (None,) * 14
         return (g0, d_n1w, d_n1b, d_qkv_w, d_qkv_b if ctx.has_qkv_bias else None, d_table, d_proj_w, d_proj_b,
                 d_n2w, d_n2b, d_fc1_w, d_fc1_b, d_fc2_w, d_fc2_b, None)
@@ -214,6 +229,7 @@ class PatchEmbedFn(torch.autograd.Function):
     def forward(ctx, vol, conv_w, conv_b, nw, nb, w16, patch):
         rows = ops.patch_gather(vol, patch)                                    # bf16 [T, pd*ph*pw]
         y = ops.linear_fwd(rows, w16, conv_b, out_dtype=F32)                   # conv output, fp32 [T, C]
+        ctx.sink = GradSink.destinations(conv_w, conv_b, nw, nb)
         if nw is None:
             ctx.has_norm = False
             ctx.save_for_backward(rows)
@@ -230,17 +246,22 @@ class PatchEmbedFn(torch.autograd.Function):
         g = _contig_f32(g)
         dev = g.device
         C = g.shape[1]
-        d_w = torch.zeros((C, ctx.wshape.numel() // C), device=dev, dtype=F32)
-        d_b = torch.zeros(C, device=dev, dtype=F32)
+        if ctx.sink is not None:
+            d_w, d_b, d_nw, d_nb = ctx.sink
+            d_w = d_w.view(C, -1)
+        else:
+            d_w, d_b, d_nw, d_nb = zeros_like_shapes([(C, ctx.wshape.numel() // C), (C,), (C,), (C,)], dev)
         if ctx.has_norm:
             rows, y, mean, rstd, nw = ctx.saved_tensors
-            d_nw, d_nb = torch.zeros(C, device=dev, dtype=F32), torch.zeros(C, device=dev, dtype=F32)
             _, dyb = ops.layernorm_bwd(g, y, mean, rstd, nw, want_dx=False, want_bf16=True, dgamma=d_nw, dbeta=d_nb)
         else:
             (rows,) = ctx.saved_tensors
             d_nw = d_nb = None
             dyb = ops.cast_rows_bf16(g)
         ops.linear_wgrad(dyb, rows, d_w, dbias=d_b)
+        if ctx.sink is not None:
+            GradSink.done(ctx.sink)
+            return (None,) * 7
         return None, d_w.view(ctx.wshape), d_b, d_nw, d_nb, None, None
 
 
@@ -270,6 +291,7 @@ class PatchMergeFn(torch.autograd.Function):
         y, mean, rstd = ops.layernorm_fwd(xg, nw, nb)
         out = ops.linear_fwd(y, w16, None, out_dtype=F32)
         ctx.meta = (pdims, rdims, B, C, red_w.shape, w16)
+        ctx.sink = GradSink.destinations(nw, nb, red_w)
         ctx.save_for_backward(xg, mean, rstd, y, nw)
         return out
 
@@ -279,12 +301,17 @@ class PatchMergeFn(torch.autograd.Function):
         xg, mean, rstd, y, nw = ctx.saved_tensors
         dev = g.device
         gb = ops.cast_rows_bf16(_contig_f32(g))
-        d_w = torch.zeros(wshape, device=dev, dtype=F32)
+        if ctx.sink is not None:
+            d_nw, d_nb, d_w = ctx.sink
+        else:
+            d_nw, d_nb, d_w = zeros_like_shapes([(8 * C,), (8 * C,), tuple(wshape)], dev)
         ops.linear_wgrad(gb, y, d_w)
         dy = ops.linear_dgrad(gb, w16)
-        d_nw, d_nb = torch.zeros(8 * C, device=dev, dtype=F32), torch.zeros(8 * C, device=dev, dtype=F32)
         dxg, _ = ops.layernorm_bwd(dy, xg, mean, rstd, nw, dgamma=d_nw, dbeta=d_nb)
         dx = ops.merge_scatter(dxg, pdims, rdims, B, C)
+        if ctx.sink is not None:
+            GradSink.done(ctx.sink)
+            return (dx,) + (None,) * 7
         return dx, d_nw, d_nb, d_w, None, None, None, None
 
 
@@ -299,6 +326,7 @@ class NormPoolHeadFn(torch.autograd.Function):
         y, mean, rstd = ops.layernorm_fwd(x, nw, nb, out_dtype=F32)
         pooled = ops.token_mean(y, B, T, Fd)
         ctx.meta = (B, T, Fd, head_w is not None, head_b is not None)
+        ctx.sink = GradSink.destinations(nw, nb, head_w, head_b)
         if head_w is None:
             ctx.save_for_backward(x, mean, rstd, nw)
             return pooled
@@ -311,18 +339,28 @@ class NormPoolHeadFn(torch.autograd.Function):
         B, T, Fd, has_head, has_bias = ctx.meta
         g = _contig_f32(g)
         dev = g.device
+        sink = ctx.sink
         if has_head:
             x, mean, rstd, nw, pooled, head_w = ctx.saved_tensors
-            d_hw = torch.zeros_like(head_w)
-            d_hb = torch.zeros(head_w.shape[0], device=dev, dtype=F32)
+            if sink is not None:
+                d_hw = sink[2]
+                d_hb = sink[3] if has_bias else torch.zeros(head_w.shape[0], device=dev, dtype=F32)
+            else:
+                d_hw, d_hb = zeros_like_shapes([tuple(head_w.shape), (head_w.shape[0],)], dev)
             dfeat = ops.head_bwd(g, pooled, head_w, d_hw, d_hb)
         else:
             x, mean, rstd, nw = ctx.saved_tensors
             d_hw = d_hb = None
             dfeat = g
         dy = ops.token_mean_bwd(dfeat, B, T, Fd)
-        d_nw, d_nb = torch.zeros(Fd, device=dev, dtype=F32), torch.zeros(Fd, device=dev, dtype=F32)
+        if sink is not None:
+            d_nw, d_nb = sink[0], sink[1]
+        else:
+            d_nw, d_nb = zeros_like_shapes([(Fd,), (Fd,)], dev)
         dx, _ = ops.layernorm_bwd(dy, x, mean, rstd, nw, dgamma=d_nw, dbeta=d_nb)
+        if sink is not None:
+            GradSink.done(sink)
+            return (dx,) + (None,) * 6
         return dx, d_nw, d_nb, d_hw, (d_hb if has_bias else None), None, None
 
 

@@ -199,6 +199,11 @@ class SwinTransformer3DBackbone(nn.Module):
                 ps.append(layer.downsample.reduction.weight)
         return ps
 
+    def _shadow_owner(self) -> swin.WeightShadow:
+        if self._shadow is None:
+            self._shadow = swin.WeightShadow(self._gemm_params())
+        return self._shadow
+
     def forward_tokens(self, x: torch.Tensor):
         """x [B,1,D,H,W] -> (tokens fp32 [B*T, F] on the final real grid, B, T)."""
         if x.dim() != 5:
@@ -211,9 +216,7 @@ class SwinTransformer3DBackbone(nn.Module):
             x = x.float()
         x = x.contiguous()
         B = x.shape[0]
-        if self._shadow is None:
-            self._shadow = swin.WeightShadow(self._gemm_params())
-        self._shadow.refresh()
+        self._shadow_owner().refresh()
         wi = 0
         pe = self.patch_embed
         has_norm = isinstance(pe.norm, nn.LayerNorm)
@@ -253,7 +256,6 @@ class SwinTransformer3DBackbone(nn.Module):
                     s2 = swin.droppath_scale(p, B, t.device, self.training, forced)
                 bi += 1
                 cfg = swin.BlockCfg(heads=blk.num_heads, hd=C // blk.num_heads, geom=geom, tokens_per_sample=tps,
-                                    acc_key=id(blk),
                                     w16=tuple(self._shadow.view(wi + j) for j in range(4)),
                                     scale1=s1, scale2=s2)
                 if prev_cfg is not None:

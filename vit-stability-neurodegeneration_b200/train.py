@@ -2,15 +2,25 @@
 micro-batch accumulation with `no_sync()` on all but the last micro-batch, soft-target cross entropy,
 AdamW (torch fused, as the reference) or SAM(AdamW) two-pass step, EMA update.  Used by bench.py,
 `__graft_entry__.smoke()` and the tests; the reference trainer drives the same modules through `dropin/`.
+
+Two things the reference's loop cannot do and this one does:
+
+* parameter gradients are accumulated by the kernels straight into one flat arena (`swin.GradSink` +
+  `ddp.GradAllReduce`): no per-parameter `grad += new`, no per-block zero fills, one fill per optimiser pass;
+* the forward + loss + backward of a micro-batch is captured once in a CUDA graph and replayed (shapes are static;
+  DropPath draws its factors from the graph-safe Philox stream), so a micro-batch costs one host call instead of
+  ~280 Python -> ctypes launches.  The data-parallel exchange then starts when the last replay has been enqueued.
 """
 from __future__ import annotations
 
 from contextlib import nullcontext
-from typing import Callable, List, Optional, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 
+from .ddp import GradAllReduce
 from .optim import SAM, EMAModel
+from .swin import GradSink
 
 
 def soft_target_ce(logits: torch.Tensor, target: torch.Tensor, smoothing: float = 0.1) -> torch.Tensor:
@@ -33,12 +43,28 @@ def param_groups(model: torch.nn.Module):
 
 
 class TrainStep:
+    """`step(batches)` = one optimiser step over the given micro-batches `[(x [B,1,D,H,W], y [B,K] soft labels)]`.
+
+    ddp_model   a torch DistributedDataParallel wrap of `model`: gradients then travel through autograd and the
+                reducer's hooks exactly as in the reference trainer (no in-place accumulation, no graph)
+    grad_sync   a `ddp.GradAllReduce` over `model.parameters()` built by the caller (N > 1); without one the step
+                builds its own arena (world size 1: nothing is exchanged)
+    graph       capture forward + loss + backward of a micro-batch in a CUDA graph and replay it
+    """
+
     def __init__(self, model: torch.nn.Module, *, lr: float = 1e-4, weight_decay: float = 0.05, use_sam: bool = False,
                  sam_rho: float = 0.05, use_ema: bool = True, ema_decay: float = 0.999, smoothing: float = 0.1,
-                 ddp_model: Optional[torch.nn.Module] = None, grad_sync=None):
+                 ddp_model: Optional[torch.nn.Module] = None, grad_sync: Optional[GradAllReduce] = None,
+                 graph: bool = False):
         self.module = model                       # the bare module (EMA / parameters)
         self.model = ddp_model if ddp_model is not None else model   # what forward is called on
-        self.grad_sync = grad_sync                # vsn_b200.ddp.GradAllReduce (bucketed NCCL all-reduce) or None
+        self.autograd_grads = ddp_model is not None
+        if self.autograd_grads:
+            if graph or grad_sync is not None:
+                raise ValueError("torch DDP owns the gradients: no grad_sync / graph with ddp_model")
+            self.grad_sync = None
+        else:
+            self.grad_sync = grad_sync if grad_sync is not None else GradAllReduce(model.parameters())
         groups = param_groups(model)
         if use_sam:
             self.opt = SAM(groups, torch.optim.AdamW, rho=sam_rho, adaptive=False, lr=lr, weight_decay=weight_decay,
@@ -48,30 +74,103 @@ class TrainStep:
         self.use_sam = use_sam
         self.ema = EMAModel(model=model, decay=ema_decay) if use_ema else None
         self.smoothing = smoothing
+        self.use_graph = graph
+        self._graph = None            # (torch.cuda.CUDAGraph, static x, static y, static loss)
+        self._graph_key = None
+        self.graph_kernel_nodes = 0
+        self.graph_replays = 0
+        self._shadows = [m._shadow_owner() for m in model.modules() if hasattr(m, "_shadow_owner")]
+
+    # ------------------------------------------------------------------ one micro-batch
+    def _fwd_bwd(self, x: torch.Tensor, y: torch.Tensor, n: int) -> torch.Tensor:
+        loss = soft_target_ce(self.model(x), y, self.smoothing) / n
+        loss.backward()
+        return loss.detach()
+
+    def _capture(self, x: torch.Tensor, y: torch.Tensor, n: int) -> None:
+        """Warm up on a side stream (allocator, plans, lazily built tables), then capture one micro-batch."""
+        sx, sy = torch.empty_like(x), torch.empty_like(y)
+        sx.copy_(x)
+        sy.copy_(y)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._fwd_bwd(sx, sy, n)
+        torch.cuda.current_stream().wait_stream(side)
+        from . import _lib
+        g = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(g):
+            sl = self._fwd_bwd(sx, sy, n)
+        self.graph_kernel_nodes = _lib.launch_count() - n0     # library kernels one replay launches
+        self.grad_sync.zero_grad()                 # warm-up and capture passes left their sums in the arena
+        self._graph = (g, sx, sy, sl)
+        self._graph_key = (tuple(x.shape), x.dtype, tuple(y.shape), y.dtype, n)
+
+    def _refresh_weights(self) -> None:
+        for sh in self._shadows:
+            sh.refresh(force=True)
 
     def _accumulate(self, batches: Sequence[Tuple[torch.Tensor, torch.Tensor]]) -> torch.Tensor:
         n = len(batches)
+        if self.autograd_grads:
+            total = None
+            for i, (x, y) in enumerate(batches):
+                ctx = nullcontext() if i == n - 1 or not hasattr(self.model, "no_sync") else self.model.no_sync()
+                with ctx:
+                    loss = self._fwd_bwd(x, y, n)
+                total = loss if total is None else total + loss
+            return total
+        gs = self.grad_sync
         total = None
-        from .swin import GradAccumulation
-        for i, (x, y) in enumerate(batches):
-            last = i == n - 1
-            GradAccumulation.begin(final=last, first=i == 0)   # block gradients are summed in-kernel over the micro-batches
-            if self.grad_sync is not None:
-                ctx = nullcontext() if last else self.grad_sync.no_sync()
+        holds = [(sh, sh.hold) for sh in self._shadows]
+        GradSink.enabled = True
+        try:
+            # the bf16 weight shadow is refreshed once per pass: the masters do not change between micro-batches
+            self._refresh_weights()
+            for sh, _ in holds:
+                sh.hold = True
+            if self.use_graph:
+                GradSink.notify = None
+                x0, y0 = batches[0]
+                key = (tuple(x0.shape), x0.dtype, tuple(y0.shape), y0.dtype, n)
+                for x, y in batches[1:]:
+                    if (tuple(x.shape), x.dtype, tuple(y.shape), y.dtype, n) != key:
+                        raise ValueError("graph mode needs micro-batches of one shape and dtype")
+                if self._graph is None or self._graph_key != key:
+                    self._capture(x0, y0, n)       # before anything of this pass has been accumulated
+                g, sx, sy, sl = self._graph
+                for x, y in batches:
+                    if x.data_ptr() != sx.data_ptr():
+                        sx.copy_(x, non_blocking=True)
+                    if y.data_ptr() != sy.data_ptr():
+                        sy.copy_(y, non_blocking=True)
+                    g.replay()
+                    self.graph_replays += 1
+                    total = sl.clone() if total is None else total + sl
+                gs.reduce_all()
             else:
-                ctx = nullcontext() if last or not hasattr(self.model, "no_sync") else self.model.no_sync()
-            with ctx:
-                loss = soft_target_ce(self.model(x), y, self.smoothing) / n
-                loss.backward()
-            total = loss.detach() if total is None else total + loss.detach()
-        GradAccumulation.end()
-        if self.grad_sync is not None:
-            self.grad_sync.finish()               # gradients are now the cross-rank mean
+                for i, (x, y) in enumerate(batches):
+                    last = i == n - 1
+                    # buckets are reduced as the last micro-batch's backward completes them
+                    GradSink.notify = (lambda grads: [gs.mark_ready(g) for g in grads]) if last else None
+                    loss = self._fwd_bwd(x, y, n)
+                    total = loss if total is None else total + loss
+        finally:
+            GradSink.enabled, GradSink.notify = False, None
+            for sh, h in holds:
+                sh.hold = h
+        gs.finish()                               # gradients are now the cross-rank mean
         return total
+
+    def input_buffers(self) -> Optional[Tuple[torch.Tensor, torch.Tensor]]:
+        """Graph mode: the captured micro-batch's static (x, y) buffers (None before the first step)."""
+        return None if self._graph is None else (self._graph[1], self._graph[2])
 
     def _zero_grad(self) -> None:
         if self.grad_sync is not None:
-            self.grad_sync.zero_grad()            # .grad tensors are views into the flat buckets: keep them
+            self.grad_sync.zero_grad()            # .grad tensors are views into the flat arena: keep them
         else:
             self.opt.zero_grad(set_to_none=True)
 

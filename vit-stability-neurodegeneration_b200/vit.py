@@ -5,7 +5,7 @@ from __future__ import annotations
 import torch
 
 from . import ops
-from .swin import _contig_f32
+from .swin import GradSink, _contig_f32, zeros_like_shapes
 
 F32, BF16 = torch.float32, torch.bfloat16
 
@@ -27,6 +27,7 @@ class ViTEmbedFn(torch.autograd.Function):
             raise ValueError(f"pos_embedding has {pos.shape[1]} positions, input needs {T + 1}")
         x = ops.vit_assemble(e, cls.reshape(-1), pos.reshape(pos.shape[1], C), B, T, C)
         ctx.meta = (B, T, C, w16, lin_w.shape, cls.shape, pos.shape)
+        ctx.sink = GradSink.destinations(ln1w, ln1b, lin_w, lin_b, ln2w, ln2b, cls, pos)
         ctx.save_for_backward(rows, m1, r1, y1, z, m2, r2, ln1w, ln2w)
         return x
 
@@ -37,19 +38,23 @@ class ViTEmbedFn(torch.autograd.Function):
         g = _contig_f32(g)
         dev = g.device
         P = rows.shape[1]
-        zeros = lambda *s: torch.zeros(s, device=dev, dtype=F32)  # noqa: E731
-        d_cls, d_pos = zeros(C), zeros(pos_shape[1], C)
+        if ctx.sink is not None:
+            d_ln1w, d_ln1b, d_lin_w, d_lin_b, d_ln2w, d_ln2b, d_cls, d_pos = ctx.sink
+            d_cls, d_pos = d_cls.view(C), d_pos.view(pos_shape[1], C)
+        else:
+            d_ln1w, d_ln1b, d_lin_w, d_lin_b, d_ln2w, d_ln2b, d_cls, d_pos = zeros_like_shapes(
+                [(P,), (P,), tuple(wshape), (C,), (C,), (C,), (C,), (pos_shape[1], C)], dev)
         ops.vit_assemble_bwd(g, d_cls, d_pos, B, T, C)
         # gradient wrt the patch embeddings = rows 1.. of every sample (a shifted crop of the token axis)
         demb = ops.grid_copy(g.view(-1)[C:], (T + 1, 1, 1), (T, 1, 1), B, C)
-        d_ln2w, d_ln2b = zeros(C), zeros(C)
         ops.ln_param_grad(demb, z, m2, r2, d_ln2w, d_ln2b)
         _, dzb = ops.layernorm_bwd(demb, z, m2, r2, ln2w, want_dx=False, want_bf16=True)
-        d_lin_b, d_lin_w = zeros(C), zeros(*wshape)
         ops.linear_wgrad(dzb, y1, d_lin_w, dbias=d_lin_b)
         dy1 = ops.linear_dgrad(dzb, w16)
-        d_ln1w, d_ln1b = zeros(P), zeros(P)
         ops.ln_param_grad(dy1, rows, m1, r1, d_ln1w, d_ln1b)
+        if ctx.sink is not None:
+            GradSink.done(ctx.sink)
+            return (None,) * 11
         return (None, d_ln1w, d_ln1b, d_lin_w, d_lin_b, d_ln2w, d_ln2b, d_cls.view(cls_shape), d_pos.view(pos_shape),
                 None, None)
 
@@ -68,6 +73,7 @@ class ViTHeadFn(torch.autograd.Function):
         y, mean, rstd = ops.layernorm_fwd(feat_in, nw, nb, out_dtype=F32)
         logits = ops.head_fwd(y, head_w, head_b)
         ctx.meta = (B, N, C, pool)
+        ctx.sink = GradSink.destinations(nw, nb, head_w, head_b)
         ctx.save_for_backward(x if pool == "cls" else feat_in, mean, rstd, nw, y, head_w)
         return logits
 
@@ -77,10 +83,11 @@ class ViTHeadFn(torch.autograd.Function):
         xin, mean, rstd, nw, y, head_w = ctx.saved_tensors
         g = _contig_f32(g)
         dev = g.device
-        d_hw = torch.zeros_like(head_w)
-        d_hb = torch.zeros(head_w.shape[0], device=dev, dtype=F32)
+        if ctx.sink is not None:
+            d_nw, d_nb, d_hw, d_hb = ctx.sink
+        else:
+            d_nw, d_nb, d_hw, d_hb = zeros_like_shapes([(C,), (C,), tuple(head_w.shape), (head_w.shape[0],)], dev)
         dy = ops.head_bwd(g, y, head_w, d_hw, d_hb)
-        d_nw, d_nb = torch.zeros(C, device=dev, dtype=F32), torch.zeros(C, device=dev, dtype=F32)
         if pool == "cls":
             feat_in = xin.view(B, N, C)[:, 0]
             ops.ln_param_grad(dy, feat_in, mean, rstd, d_nw, d_nb)
@@ -90,4 +97,7 @@ class ViTHeadFn(torch.autograd.Function):
             ops.ln_param_grad(dy, xin, mean, rstd, d_nw, d_nb)
             dfeat, _ = ops.layernorm_bwd(dy, xin, mean, rstd, nw)
             dx = ops.token_mean_bwd(dfeat, B, N, C)
+        if ctx.sink is not None:
+            GradSink.done(ctx.sink)
+            return (dx,) + (None,) * 7
         return dx, d_nw, d_nb, d_hw, d_hb, None, None, None

@@ -126,6 +126,11 @@ class ViT(nn.Module):
             ps += [attn.to_qkv.weight, attn.to_out[0].weight, ff.net[1].weight, ff.net[4].weight]
         return ps
 
+    def _shadow_owner(self) -> swin.WeightShadow:
+        if self._shadow is None:
+            self._shadow = swin.WeightShadow(self._gemm_params())
+        return self._shadow
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if type(x) is not torch.Tensor:
             x = x.as_subclass(torch.Tensor)
@@ -138,9 +143,7 @@ class ViT(nn.Module):
         for s, p in zip(x.shape[2:], self.patch_size):
             if s % p:
                 raise ValueError(f"input {tuple(x.shape)} is not divisible by the patch size {self.patch_size}")
-        if self._shadow is None:
-            self._shadow = swin.WeightShadow(self._gemm_params())
-        self._shadow.refresh()
+        self._shadow_owner().refresh()
         pe = self.to_patch_embedding
         t = vit.ViTEmbedFn.apply(x, pe[1].weight, pe[1].bias, pe[2].weight, pe[2].bias, pe[3].weight, pe[3].bias,
                                  self.cls_token, self.pos_embedding, self._shadow.view(0), self.patch_size)
@@ -150,7 +153,7 @@ class ViT(nn.Module):
         for layer in self.transformer.layers:
             attn, ff, dp = layer[0], layer[1], layer[4]
             p = dp.drop_prob if isinstance(dp, DropPath) else 0.0
-            cfg = swin.BlockCfg(heads=attn.heads, hd=attn.dim_head, geom=None, tokens_per_sample=N, S=B, N=N, acc_key=id(attn),
+            cfg = swin.BlockCfg(heads=attn.heads, hd=attn.dim_head, geom=None, tokens_per_sample=N, S=B, N=N,
                                 w16=tuple(self._shadow.view(wi + j) for j in range(4)),
                                 scale1=swin.droppath_scale(p, B, t.device, self.training, forced),
                                 scale2=swin.droppath_scale(p, B, t.device, self.training, forced))
