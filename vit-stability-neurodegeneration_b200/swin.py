@@ -86,6 +86,23 @@ class GradSink:
     notify = None       # callable(list of .grad views) or None
 
     @classmethod
+    def wrap(cls, p):
+        """Model code hands every parameter to the Functions through this.  Enabled: a fresh leaf that shares the
+        parameter's storage and carries the `.grad` view the kernels accumulate into.  (A fresh leaf per forward also
+        keeps autograd's per-parameter AccumulateGrad nodes -- which remember the stream they were created on and
+        stay alive as long as any earlier graph does -- out of a CUDA-graph capture: a node from an eager pass would
+        make the engine record an event on the default stream in the middle of the capture.)"""
+        if not cls.enabled or p is None:
+            return p
+        g = p.grad
+        if g is None or g.dtype != F32 or not g.is_contiguous() or g.shape != p.shape:
+            raise RuntimeError("GradSink needs a persistent contiguous fp32 .grad on every parameter "
+                               "(ddp.GradAllReduce provides them)")
+        q = p.detach().requires_grad_(True)
+        q._vsn_sink = g
+        return q
+
+    @classmethod
     def destinations(cls, *params):
         """Called in forward: the `.grad` views the unit's backward will accumulate into, or None."""
         if not cls.enabled:
@@ -95,10 +112,9 @@ class GradSink:
             if p is None:
                 out.append(None)
                 continue
-            g = p.grad
-            if g is None or g.dtype != F32 or not g.is_contiguous() or g.shape != p.shape:
-                raise RuntimeError("GradSink needs a persistent contiguous fp32 .grad on every parameter "
-                                   "(ddp.GradAllReduce provides them)")
+            g = getattr(p, "_vsn_sink", None)
+            if g is None:
+                raise RuntimeError("GradSink is enabled but a parameter reached a Function without GradSink.wrap()")
             out.append(g)
         return out
 

@@ -220,8 +220,9 @@ class SwinTransformer3DBackbone(nn.Module):
         wi = 0
         pe = self.patch_embed
         has_norm = isinstance(pe.norm, nn.LayerNorm)
-        t = swin.PatchEmbedFn.apply(x, pe.proj.weight, pe.proj.bias, pe.norm.weight if has_norm else None,
-                                    pe.norm.bias if has_norm else None, self._shadow.view(wi), pe.patch_size)
+        W = swin.GradSink.wrap
+        t = swin.PatchEmbedFn.apply(x, W(pe.proj.weight), W(pe.proj.bias), W(pe.norm.weight) if has_norm else None,
+                                    W(pe.norm.bias) if has_norm else None, self._shadow.view(wi), pe.patch_size)
         wi += 1
         real = tuple(-(-s // p) for s, p in zip(x.shape[2:], pe.patch_size))
         forced = DropPath.forced_masks
@@ -265,13 +266,13 @@ class SwinTransformer3DBackbone(nn.Module):
                 prev_cfg = cfg
                 wi += 4
                 a = blk.attn
-                t = swin.SwinBlockFn.apply(t, blk.norm1.weight, blk.norm1.bias, a.qkv.weight, a.qkv.bias,
-                                           a.relative_position_bias_table, a.proj.weight, a.proj.bias,
-                                           blk.norm2.weight, blk.norm2.bias, blk.mlp[0].weight, blk.mlp[0].bias,
-                                           blk.mlp[3].weight, blk.mlp[3].bias, cfg)
+                t = swin.SwinBlockFn.apply(t, W(blk.norm1.weight), W(blk.norm1.bias), W(a.qkv.weight), W(a.qkv.bias),
+                                           W(a.relative_position_bias_table), W(a.proj.weight), W(a.proj.bias),
+                                           W(blk.norm2.weight), W(blk.norm2.bias), W(blk.mlp[0].weight),
+                                           W(blk.mlp[0].bias), W(blk.mlp[3].weight), W(blk.mlp[3].bias), cfg)
             if layer.downsample is not None:
                 ds = layer.downsample
-                t = swin.PatchMergeFn.apply(t, ds.norm.weight, ds.norm.bias, ds.reduction.weight,
+                t = swin.PatchMergeFn.apply(t, W(ds.norm.weight), W(ds.norm.bias), W(ds.reduction.weight),
                                             self._shadow.view(wi), pdims, real, B)
                 wi += 1
                 real = tuple((r + 1) // 2 for r in real)
@@ -282,7 +283,8 @@ class SwinTransformer3DBackbone(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         t, B, real = self.forward_tokens(x)
         T = real[0] * real[1] * real[2]
-        return swin.NormPoolHeadFn.apply(t, self.norm.weight, self.norm.bias, None, None, B, T)
+        W = swin.GradSink.wrap
+        return swin.NormPoolHeadFn.apply(t, W(self.norm.weight), W(self.norm.bias), None, None, B, T)
 
 
 class SwinTransformer(nn.Module):
@@ -304,9 +306,11 @@ class SwinTransformer(nn.Module):
         bb = self.backbone
         t, B, real = bb.forward_tokens(x)
         T = real[0] * real[1] * real[2]
+        W = swin.GradSink.wrap
         if isinstance(self.head, nn.Linear):
-            return swin.NormPoolHeadFn.apply(t, bb.norm.weight, bb.norm.bias, self.head.weight, self.head.bias, B, T)
-        return swin.NormPoolHeadFn.apply(t, bb.norm.weight, bb.norm.bias, None, None, B, T)
+            return swin.NormPoolHeadFn.apply(t, W(bb.norm.weight), W(bb.norm.bias), W(self.head.weight),
+                                             W(self.head.bias), B, T)
+        return swin.NormPoolHeadFn.apply(t, W(bb.norm.weight), W(bb.norm.bias), None, None, B, T)
 
 
 def _variant(name: str):

@@ -145,8 +145,10 @@ class ViT(nn.Module):
                 raise ValueError(f"input {tuple(x.shape)} is not divisible by the patch size {self.patch_size}")
         self._shadow_owner().refresh()
         pe = self.to_patch_embedding
-        t = vit.ViTEmbedFn.apply(x, pe[1].weight, pe[1].bias, pe[2].weight, pe[2].bias, pe[3].weight, pe[3].bias,
-                                 self.cls_token, self.pos_embedding, self._shadow.view(0), self.patch_size)
+        W = swin.GradSink.wrap
+        t = vit.ViTEmbedFn.apply(x, W(pe[1].weight), W(pe[1].bias), W(pe[2].weight), W(pe[2].bias), W(pe[3].weight),
+                                 W(pe[3].bias), W(self.cls_token), W(self.pos_embedding), self._shadow.view(0),
+                                 self.patch_size)
         N = t.shape[0] // B
         wi = 1
         forced = DropPath.forced_masks
@@ -158,11 +160,12 @@ class ViT(nn.Module):
                                 scale1=swin.droppath_scale(p, B, t.device, self.training, forced),
                                 scale2=swin.droppath_scale(p, B, t.device, self.training, forced))
             wi += 4
-            t = swin.SwinBlockFn.apply(t, attn.norm.weight, attn.norm.bias, attn.to_qkv.weight, None, None,
-                                       attn.to_out[0].weight, attn.to_out[0].bias, ff.net[0].weight, ff.net[0].bias,
-                                       ff.net[1].weight, ff.net[1].bias, ff.net[4].weight, ff.net[4].bias, cfg)
-        return vit.ViTHeadFn.apply(t, self.mlp_head[0].weight, self.mlp_head[0].bias, self.mlp_head[1].weight,
-                                   self.mlp_head[1].bias, B, N, self.pool)
+            t = swin.SwinBlockFn.apply(t, W(attn.norm.weight), W(attn.norm.bias), W(attn.to_qkv.weight), None, None,
+                                       W(attn.to_out[0].weight), W(attn.to_out[0].bias), W(ff.net[0].weight),
+                                       W(ff.net[0].bias), W(ff.net[1].weight), W(ff.net[1].bias), W(ff.net[4].weight),
+                                       W(ff.net[4].bias), cfg)
+        return vit.ViTHeadFn.apply(t, W(self.mlp_head[0].weight), W(self.mlp_head[0].bias), W(self.mlp_head[1].weight),
+                                   W(self.mlp_head[1].bias), B, N, self.pool)
 
 
 class ViTX(ViT):
