@@ -29,7 +29,8 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, extra_flags=(), only=None) -> str:
+    """extra_flags / only (source names) serve measurement builds, e.g. `-DVSN_MBAR_HINT_NS=0` for wattn_tc.cu."""
     if not force and not needs_build():
         return LIB
     nvcc = _nvcc()
@@ -38,7 +39,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-I", HERE, "-c", os.path.join(HERE, src), "-o", obj]
+        if only is not None and src not in only and os.path.exists(obj):
+            return obj
+        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-I", HERE, "-c", os.path.join(HERE, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -59,4 +62,6 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    extra = [a for a in sys.argv[1:] if a.startswith("-D")]
+    only = [a[len("--only="):] for a in sys.argv[1:] if a.startswith("--only=")] or None
+    print(build(force="--force" in sys.argv or bool(extra), verbose="-v" in sys.argv, extra_flags=extra, only=only))

@@ -26,8 +26,26 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// One probe of the phase.  With a suspend-time hint the hardware may keep the thread asleep up to that many
+// nanoseconds (it is woken by the arrival that completes the phase), so a waiting warp re-issues the probe loop far
+// less often: in the attention kernels a third of all issued instructions were such probes (BRA / SYNCS / YIELD),
+// taking issue slots from the warps that had work.  VSN_MBAR_HINT_NS = 0 compiles the plain form.
+#ifndef VSN_MBAR_HINT_NS
+#define VSN_MBAR_HINT_NS 20000
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#if VSN_MBAR_HINT_NS > 0
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(static_cast<uint32_t>(VSN_MBAR_HINT_NS))
+      : "memory");
+#else
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -37,6 +55,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
 }
 // Bounded waits: a protocol bug traps (the launch fails loudly) instead of hanging the GPU.
