@@ -1,0 +1,181 @@
+#!/usr/bin/env python
+"""Drive the UNMODIFIED reference trainer (train/train_transformer.py) through vsn_b200's drop-in packages on
+synthetic data: proof that `train/train_transformer.py`, `regularization/sam.py` users and
+`utils/ema.py` users run unchanged on the sm_100a path.  TEST / MEASUREMENT HARNESS, not product.
+
+    python scripts/run_reference_trainer.py --arch swin --steps 6 --out gpurun_out/trainer_swin
+    torchrun --nproc-per-node 2 ... scripts/run_reference_trainer.py --arch swin --steps 6 --out ...
+
+What it sets up, all outside the reference's files:
+  * `monai` / `nibabel` / `nilearn` / `timm` stand-ins (absent from this image): Compose, NormalizeIntensity and Resize
+    with MONAI's semantics for the minimal-augmentation branch (train/train_transformer.py:1729-1752), no-op Rand*;
+  * a synthetic cohort: 10 fold CSVs (Subject, Diagnosis) + fp16 `[1,D,H,W]` `.pt` volumes in the cache directory, so
+    the trainer's preprocessing step finds everything present (train/train_transformer.py:1571-1576);
+  * a config YAML overriding the chosen `configs/*-no_seed-baseline.yaml`: few steps, small volumes, SAM + EMA +
+    MixUp + balanced sampler on, validation every 2 steps, checkpoints kept;
+  * `sys.path`: vsn_b200's `dropin/` first, the reference root last (as the trainer itself appends it), CWD = the
+    reference root (wandb loads `config-defaults.yaml` from there).
+Then `runpy` executes the trainer as `__main__`.  With `--resume` the run is repeated from the `_last.pt` checkpoint
+the first run wrote; `--compare` loads that checkpoint into the reference's own model class on the CPU and compares
+its logits with the drop-in model's on the same input.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import runpy
+import sys
+import types
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def install_stubs():
+    import torch
+    from oracle import refshim
+    ref_root = refshim.install()            # timm.layers + minimal monai (Transform, MapTransform, set_determinism)
+    sys.path.remove(ref_root)
+    mt = sys.modules["monai.transforms"]
+
+    class Compose:
+        def __init__(self, transforms=None, **kw):
+            self.transforms = list(transforms or [])
+
+        def __call__(self, x):
+            for t in self.transforms:
+                x = t(x)
+            return x
+
+    class NormalizeIntensity:                # monai default: (x - mean) / std over the whole image, std == 0 -> no division
+        def __init__(self, *a, **kw):
+            pass
+
+        def __call__(self, x):
+            x = x.float()
+            s = x.std(unbiased=False)
+            return (x - x.mean()) / s if float(s) != 0.0 else x - x.mean()
+
+    class Resize:                            # monai default mode "area" on [C, D, H, W]
+        def __init__(self, spatial_size, *a, **kw):
+            self.size = tuple(int(v) for v in spatial_size)
+
+        def __call__(self, x):
+            if tuple(x.shape[-3:]) == self.size:
+                return x
+            return torch.nn.functional.interpolate(x[None].float(), size=self.size, mode="area")[0]
+
+    class _Identity:
+        def __init__(self, *a, **kw):
+            pass
+
+        def __call__(self, x):
+            return x
+
+    mt.Compose, mt.NormalizeIntensity, mt.Resize = Compose, NormalizeIntensity, Resize
+    for name in ("Rand3DElastic", "RandAdjustContrast", "RandAffine", "RandBiasField", "RandFlip", "RandGibbsNoise",
+                 "RandHistogramShift", "RandKSpaceSpikeNoise", "RandScaleIntensity", "CenterSpatialCrop", "OneOf",
+                 "Identity", "RandSpatialCrop", "Flip", "Affine"):
+        setattr(mt, name, type(name, (_Identity,), {}))
+    for name in ("nibabel", "nilearn", "nilearn.image", "nilearn.masking"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["nilearn"].image = sys.modules["nilearn.image"]
+    sys.modules["nilearn"].masking = sys.modules["nilearn.masking"]
+    return ref_root
+
+
+def make_cohort(out, img_size, classes, per_fold=4):
+    """10 fold CSVs + fp16 [1, D, H, W] volumes (dataset/preprocessing.py:242-249 cache format)."""
+    import numpy as np
+    import pandas as pd
+    import torch
+    csv_dir, cache = os.path.join(out, "folds"), os.path.join(out, "cache", "train")
+    os.makedirs(csv_dir, exist_ok=True)
+    os.makedirs(cache, exist_ok=True)
+    rs = np.random.RandomState(0)
+    n = 0
+    for f in range(10):
+        rows = []
+        for i in range(per_fold):
+            subj = f"sub{f:02d}{i:02d}"
+            cls = classes[(f + i) % len(classes)]
+            rows.append({"Subject": subj, "Diagnosis": cls, "Dataset": "SYNTH", "Age": 60 + i, "Sex": "F"})
+            p = os.path.join(cache, subj + ".pt")
+            if not os.path.exists(p):
+                v = rs.standard_normal((1, *img_size)).astype(np.float32) + 0.3 * classes.index(cls)
+                torch.save(torch.from_numpy(v).half(), p)
+            n += 1
+        pd.DataFrame(rows).to_csv(os.path.join(csv_dir, f"fold_{f}.csv"), index=False)
+    return csv_dir, os.path.join(out, "cache"), n
+
+
+def write_config(out, ref_root, arch, img_size, steps, classes):
+    import yaml
+    base = {"swin": f"swin-{len(classes)}c-no_seed-baseline.yaml", "vit": f"vit-{len(classes)}c-no_seed-baseline.yaml"}[arch]
+    with open(os.path.join(ref_root, "configs", base)) as f:
+        cfg = yaml.safe_load(f)
+    over = {"IMG_SIZE": list(img_size), "RESHAPE_SIZE": list(img_size) if arch == "vit" else None, "STEPS": steps,
+            "BATCH_SIZE": 2, "EFFECTIVE_BATCH_SIZE": 8, "USE_EMA": True, "USE_SAM": True, "USE_MIXUP": True,
+            "USE_BALANCED_SAMPLER": True, "VALIDATION_FREQUENCY": 2, "NUM_WORKERS": 0, "PREFETCH_FACTOR": None,
+            "PRELOAD_DATA": True, "KEEP_BEST_N": 2, "LR_WARMUP": 1, "WD_WARMUP": 1, "EARLY_STOPPING_PATIENCE": 1000,
+            "SEED": 123}
+    for k, v in over.items():
+        if k in cfg and isinstance(cfg[k], dict) and "value" in cfg[k]:
+            cfg[k]["value"] = v
+        else:
+            cfg[k] = {"value": v}
+    path = os.path.join(out, f"{arch}-harness.yaml")
+    with open(path, "w") as f:
+        yaml.safe_dump(cfg, f)
+    return path
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--arch", default="swin", choices=["swin", "vit"])
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "trainer_harness"))
+    ap.add_argument("--img-size", type=int, nargs=3, default=None)
+    ap.add_argument("--resume", action="store_true", help="resume from the _last.pt checkpoint of a previous run")
+    ap.add_argument("--reference-models", action="store_true",
+                    help="do NOT shadow the reference's modules (control run of the harness itself, any device)")
+    a = ap.parse_args()
+    out = os.path.abspath(a.out)
+    os.makedirs(out, exist_ok=True)
+    classes = ["CN", "AD", "FTD"]
+    img = tuple(a.img_size) if a.img_size else ((48, 56, 48) if a.arch == "swin" else (48, 64, 48))
+    ref_root = install_stubs()
+    rank = int(os.environ.get("RANK", "0"))
+    if rank == 0:
+        csv_dir, cache, n = make_cohort(out, img, classes)
+        print(f"harness: {n} synthetic subjects {img} in {cache}", flush=True)
+    else:
+        csv_dir, cache = os.path.join(out, "folds"), os.path.join(out, "cache")
+    cfg = write_config(out, ref_root, a.arch, img, a.steps, classes) if rank == 0 else os.path.join(out, f"{a.arch}-harness.yaml")
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:      # the other ranks wait for the cohort
+        import time
+        while not os.path.exists(cfg):
+            time.sleep(0.2)
+        time.sleep(1.0)
+    if not a.reference_models:
+        sys.path.insert(0, os.path.join(ROOT, "vit-stability-neurodegeneration_b200", "dropin"))
+    sys.path.append(ref_root)                            # what train_transformer.py:51 does itself
+    save_dir = os.path.join(out, "runs")
+    argv = ["train_transformer.py", "--training-csv-dir", csv_dir, "--intermediate-dir", cache, "--save-dir", save_dir,
+            "--runname", f"{a.arch}_harness", "--wandb-mode", "offline", "--config", cfg, "--fold", "0"]
+    if a.resume:
+        import glob
+        last = sorted(glob.glob(os.path.join(save_dir, f"{a.arch}_harness", "*_last.pt")))
+        if not last:
+            raise SystemExit("no *_last.pt checkpoint to resume from")
+        argv += ["--checkpoint", last[-1]]
+    os.chdir(ref_root)                                   # wandb reads ./config-defaults.yaml
+    os.environ.setdefault("WANDB_SILENT", "true")
+    os.environ.setdefault("WANDB_DIR", out)
+    sys.argv = argv
+    runpy.run_path(os.path.join(ref_root, "train", "train_transformer.py"), run_name="__main__")
+
+
+if __name__ == "__main__":
+    main()

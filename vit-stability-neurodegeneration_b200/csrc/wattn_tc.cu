@@ -497,18 +497,26 @@ int wattn_tc_fwd(const WinAttnArgs& a, cudaStream_t stream) {
 
 // =========================================== backward =============================================
 // CTA = (head, half kh of the window's keys), persistent over a group of windows.  TMEM lanes are KEYS:
-//   S^T = K_half Q^T and dP^T = V_half dO^T are computed per sub-tile of 32 queries (two 64-column buffers),
+//   S^T = K_half Q^T and dP^T = V_half dO^T are computed per sub-tile of 16 queries (four 32-column buffers),
 //   the compute threads turn them into P^T = exp2(S^T*c + B^T - lse) and dS^T = P^T (dP^T - delta) in place
 //   (bf16 pairs over their own columns), which feed straight from TMEM
 //     dV += P^T dO_sub,   dK += dS^T Q_sub,   dBias[:, sub] += dS^T I16   (identity B operand: the dense
 //     bias gradient of this (head, key half) accumulates over ALL windows of the CTA in 256 TMEM columns),
 //   while a copy of dS^T in an MN-major smem tile gives dQ_half = dS K_half (two 128-query blocks).
 //   dQ is the sum of the two key halves: bf16x2 red.add into the zeroed Q block of dqkv.
-// Warps: 0-7 compute group 0 (even sub-tiles), 8-15 group 1 (odd sub-tiles; also the per-window read-out of
-// dK / dV / dQ), 16 loader, 17 MMA issuer.  Thread = (key row, 16 of the sub-tile's 32 queries).
+// Warps: 0-15 = four compute groups of four warps (group g owns buffer g and the sub-tiles T = g mod 4; thread =
+// (key row, the sub-tile's 16 queries)), 16 loader, 17 MMA issuer.  The MMA warp issues S^T / dP^T three sub-tiles
+// ahead of the dV / dK / dBias MMAs, so a group that has finished a sub-tile finds its next one already in TMEM.
+// (Round 1 ran two groups on two 32-query buffers: a group's next S^T was only issued after its own arrival, so it
+// sat out the whole MMA turn-around every sub-tile -- 22 % of all samples were that one probe loop -- and only one
+// group's 8 warps were ever computing.  tcgen05.mma with the A operand in shared memory costs ~40 clk for any
+// N <= 32 (scripts/ub/mma_shapes.cu: the 4 KB A read), so the 16-query S^T / dP^T MMAs take twice the tensor time
+// of the 32-query ones: ~2600 of the ~3900 tensor clocks per window and key half, still far below the compute time.)
 constexpr int BWD_THREADS = 20 * 32;           // 16 compute warps + one warpgroup of helpers (loader, MMA issuer, two idle)
-constexpr int QS = 32;                         // queries per sub-tile
-constexpr int NSUB = NP / QS;                  // 8
+constexpr int QS = 16;                         // queries per sub-tile
+constexpr int NSUB = NP / QS;                  // 16
+constexpr int NGRP = 4;                        // compute groups = S^T / dP^T buffers
+constexpr int MMA_LAG = NGRP - 1;              // sub-tiles the S^T / dP^T MMAs run ahead of the dV / dK / dBias MMAs
 constexpr int BWD_STAGE_BYTES = 51712;         // Q 16K | dO 16K | K_half 8K | V_half 8K | lse2 1K | delta 1K | qcode 256
 constexpr int DS_TILE_BYTES = 128 * NP * 2;    // 64 KB: dS^T as MN-major A operand, 128B swizzle
 
@@ -570,16 +578,6 @@ __device__ __forceinline__ void red_add_bf16x8(bf16* addr, uint32_t a, uint32_t 
                : "memory");
 }
 
-// Per-phase cycle counters of the backward kernel: compiled in with -DVSN_WATTN_TIMING (they cost a dozen registers
-// in a kernel that runs at the 96-register cap: 0.590 -> 0.565 ms at stage 0 without them), printed when the
-// environment has VSN_WATTN_TIMING=1.
-__device__ unsigned long long* g_bwd_timing = nullptr;   // [gridDim][16]
-#ifdef VSN_WATTN_TIMING
-#define TCLK() clock64()
-#else
-#define TCLK() 0ll
-#endif
-
 template <int WD, int WH, int WW>
 __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttnArgs p, const float* __restrict__ delta_g) {
   pdl_trigger();   // the next kernel of the stream may be scheduled (it waits for this grid before reading)
@@ -593,21 +591,21 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::BARS);
   uint64_t* ld_full = bars;          // [2] loader lanes -> MMA
   uint64_t* ld_empty = bars + 2;     // [2] MMA commit -> loader
-  uint64_t* s_full = bars + 4;       // [2 buffers] MMA commit -> compute group
-  uint64_t* p_ready = bars + 6;      // [2 buffers] compute group -> MMA
-  uint64_t* ds_free = bars + 8;      // [2 query blocks] MMA commit (dQ block done) -> compute threads (smem tile half)
-  uint64_t* unit_done = bars + 10;   // MMA commit: every MMA of the window (incl. dQ) complete -> group 1
-  uint64_t* acc_read = bars + 11;    // group 1: dV / dK accumulators read out -> MMA (next window's first dV/dK MMA)
-  uint64_t* kv_done = bars + 12;     // MMA commit: dV, dK of the window complete -> group 1
-  uint64_t* dq_read = bars + 13;     // group 1: dQ accumulator read out -> MMA (next window's first dQ MMA)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* s_full = bars + 4;       // [4 buffers] MMA commit -> compute group
+  uint64_t* p_ready = bars + 8;      // [4 buffers] compute group -> MMA
+  uint64_t* ds_free = bars + 12;     // [2 query blocks] MMA commit (dQ block done) -> compute threads (smem tile half)
+  uint64_t* unit_done = bars + 14;   // MMA commit: every MMA of the window (incl. dQ) complete -> groups 2, 3
+  uint64_t* acc_read = bars + 15;    // groups 0, 1: dV / dK accumulators read out -> MMA (next window's first dV/dK MMA)
+  uint64_t* kv_done = bars + 16;     // MMA commit: dV, dK of the window complete -> groups 0, 1
+  uint64_t* dq_read = bars + 17;     // groups 2, 3: dQ accumulators read out -> MMA (next window's first dQ MMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.y, kh = blockIdx.z;
   const int n_units = (p.S - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   const int TT = n_units * NSUB;     // sub-tiles of this CTA
 
-  // TMEM map (columns): [0,256) dBias accumulator | buffer b at 256+64b: S^T [0,32) dP^T [32,64) |
+  // TMEM map (columns): [0,256) dBias accumulator | buffer b at 256+32b: S^T [0,16) dP^T [16,32) |
   //                     384.. dQ (2 x 32) | 448.. dV | 480.. dK
   constexpr uint32_t COL_BUF = 256, COL_DQ = 384, COL_DV = 448, COL_DK = 480;
 
@@ -619,9 +617,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&ld_full[i], 32);
       tc::mbar_init(&ld_empty[i], 1);
-      tc::mbar_init(&s_full[i], 1);
-      tc::mbar_init(&p_ready[i], 256);
       tc::mbar_init(&ds_free[i], 1);
+    }
+    for (int i = 0; i < NGRP; ++i) {
+      tc::mbar_init(&s_full[i], 1);
+      tc::mbar_init(&p_ready[i], 128);
     }
     tc::mbar_init(unit_done, 1);
     tc::mbar_init(acc_read, 256);
@@ -699,7 +699,6 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
       const uint64_t desc_ident = tc::make_smem_desc_sw64(tc::smem_u32(ident), 16, 512);
       const uint64_t desc_ds = tc::make_smem_desc_sw128(tc::smem_u32(ds_tile), 16384, 1024);
       const uint64_t desc_st0 = tc::make_smem_desc_sw64(tc::smem_u32(stages), 16, 512);   // stage 0, offset 0
-      long long tm_ld = 0, tm_pr = 0, tm_acc = 0, tm_t0 = TCLK(), tq;
       int pend_mb = -1, pend_st = 0;
       uint64_t pend_dst = 0;
       auto issue_dq = [&]() {
@@ -718,15 +717,15 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
         __syncwarp();
         pend_mb = -1;
       };
-      for (int T = 0; T <= TT; ++T) {
+      for (int T = 0; T < TT + MMA_LAG; ++T) {
         if (T < TT) {
-          const int n = T / NSUB, t = T % NSUB, st = n & 1, b = T & 1;
-          tq = TCLK();
+          // S^T / dP^T of sub-tile T into buffer T % 4: its previous user, sub-tile T - 4, had its dV / dK / dBias MMAs
+          // issued in the previous iteration (the tensor pipe executes in order)
+          const int n = T / NSUB, t = T % NSUB, st = n & 1, b = T & (NGRP - 1);
           if (t == 0) tc::mbar_wait(&ld_full[st], (n >> 1) & 1);
-          tm_ld += TCLK() - tq;
           tc::fence_after_sync();
           const uint64_t dst = tc::desc_advance(desc_st0, st * BWD_STAGE_BYTES);
-          const uint32_t d = tmem_base + COL_BUF + b * 64;
+          const uint32_t d = tmem_base + COL_BUF + b * 32;
           if (tc::elect_one()) {
 #pragma unroll
             for (int k = 0; k < 2; ++k)
@@ -734,54 +733,42 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
                               idesc_s, k);
 #pragma unroll
             for (int k = 0; k < 2; ++k)
-              tc::mma_bf16_ss(d + 32, tc::desc_advance(dst, 40960 + k * 32),
+              tc::mma_bf16_ss(d + 16, tc::desc_advance(dst, 40960 + k * 32),
                               tc::desc_advance(dst, 16384 + t * (QS * 64) + k * 32), idesc_s, k);
             tc::mma_commit(&s_full[b]);
           }
           __syncwarp();
         }
         issue_dq();
-        if (T >= 1) {
-          const int V = T - 1, n = V / NSUB, t = V % NSUB, st = n & 1, b = V & 1;
-          tq = TCLK();
-          tc::mbar_wait(&p_ready[b], (V >> 1) & 1);
-          tm_pr += TCLK() - tq;
-          tq = TCLK();
+        if (T >= MMA_LAG) {
+          const int V = T - MMA_LAG, n = V / NSUB, t = V % NSUB, st = n & 1, b = V & (NGRP - 1);
+          tc::mbar_wait(&p_ready[b], (V >> 2) & 1);
           if (t == 0) tc::mbar_wait(acc_read, (n & 1) ^ 1);       // previous window's dK / dV were read out
-          if (t == 3) tc::mbar_wait(dq_read, (n & 1) ^ 1);        // previous window's dQ was read out
-          tm_acc += TCLK() - tq;
+          if (t == 7) tc::mbar_wait(dq_read, (n & 1) ^ 1);        // previous window's dQ was read out
           tc::fence_after_sync();
           const uint64_t dst = tc::desc_advance(desc_st0, st * BWD_STAGE_BYTES);
-          const uint32_t a_p = tmem_base + COL_BUF + b * 64;        // P^T  (bf16 pairs: 8 columns per 16 queries, at 16*half)
-          const uint32_t a_ds = a_p + 32;                           // dS^T
+          const uint32_t a_p = tmem_base + COL_BUF + b * 32;        // P^T  (bf16 pairs: 8 columns for the 16 queries)
+          const uint32_t a_ds = a_p + 16;                           // dS^T
           if (tc::elect_one()) {
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              const uint32_t rows = (t * QS + k * 16) * 64;
-              tc::mma_bf16_ts(tmem_base + COL_DV, a_p + k * 16, tc::desc_advance(dst, 16384 + rows), idesc_kv,
-                              (t | k) ? 1u : 0u);
-              tc::mma_bf16_ts(tmem_base + COL_DK, a_ds + k * 16, tc::desc_advance(dst, rows), idesc_kv, (t | k) ? 1u : 0u);
-              tc::mma_bf16_ts(tmem_base + t * QS + k * 16, a_ds + k * 16, desc_ident, idesc_b, n ? 1u : 0u);
-            }
+            const uint32_t rows = (t * QS) * 64;
+            tc::mma_bf16_ts(tmem_base + COL_DV, a_p, tc::desc_advance(dst, 16384 + rows), idesc_kv, t ? 1u : 0u);
+            tc::mma_bf16_ts(tmem_base + COL_DK, a_ds, tc::desc_advance(dst, rows), idesc_kv, t ? 1u : 0u);
+            tc::mma_bf16_ts(tmem_base + t * QS, a_ds, desc_ident, idesc_b, n ? 1u : 0u);
             if (t == NSUB - 1) tc::mma_commit(kv_done);
           }
           __syncwarp();
           // dQ for the 128-query block that is now complete in the smem tile: eight K=16 steps that nobody waits for
           // soon -- issued in the next iteration, behind that sub-tile's S^T / dP^T (the tensor pipe runs in order)
-          if ((t & 3) == 3) { pend_mb = t >> 2; pend_dst = dst; pend_st = st; }
+          if ((t & 7) == 7) { pend_mb = t >> 3; pend_dst = dst; pend_st = st; }
         }
       }
       issue_dq();
-      if (g_bwd_timing != nullptr && lane == 0) {
-        unsigned long long* o = g_bwd_timing + ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16;
-        o[0] = TCLK() - tm_t0; o[1] = tm_ld; o[2] = tm_pr; o[3] = tm_acc; o[4] = TT;
-      }
     }
   }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     // ------------------------------------------------------------------ compute groups
-    const int g = warp >> 3, q4 = warp & 3, half = (warp >> 2) & 1;
+    const int g = warp >> 2, q4 = warp & 3;        // group = buffer; its four warps cover the four TMEM lane quadrants
     const int r = q4 * 32 + lane;                  // key row inside the half = TMEM lane
     const int j = kh * 128 + r;                    // key token of the window
     const int jb = j < N ? j : N - 1;
@@ -796,26 +783,25 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
     const uint32_t ds_row = (r >> 3) * 1024 + (r & 7) * 128;
     WinCoord wc = {};
     uint32_t ck4 = 0;
-    long long tc_wait = 0, tc_ld = 0, tc_math = 0, tc_st = 0, tc_ro = 0, tc_q;
     WinCoord wc_prev = {};
 
-    // Read-out of window rn (group 1 only), run one sub-tile into the NEXT window so that kv_done / unit_done have
-    // long fired and nothing here waits.
+    // Read-out of window rn, one accumulator per group (0: dV, 1: dK, 2 / 3: the two dQ blocks), run one sub-tile into
+    // the NEXT window so that kv_done / unit_done have long fired and nothing here waits.
     auto readout = [&](int rn, const WinCoord& rwc) {
-        // ---- window read-out.  dV / dK rows of this key half: direct stores, released as soon as they are in
-        // registers (the next window's first MMA overwrites them); dQ partial: bf16 red.add (REDG.BF16x8) into the
-        // zeroed Q block, needed back only at the next window's 4th sub-tile.
-        uint32_t acc[32];
+      uint32_t acc[32];
+      if (g < 2) {
+        // dV / dK rows of this key half: direct stores, released as soon as they are in registers (the next window's
+        // first MMA overwrites them)
         tc::mbar_wait(kv_done, rn & 1);
         tc::fence_after_sync();
-        tc::tmem_ld_32x32b_x32(tmem_base + lane_addr + (half ? COL_DK : COL_DV), acc);
+        tc::tmem_ld_32x32b_x32(tmem_base + lane_addr + (g ? COL_DK : COL_DV), acc);
         tc::tmem_ld_wait();
         tc::fence_before_sync();
         tc::mbar_arrive(acc_read);
         if (j < N) {
           const TokenGeom gk = token_geom_w<WD, WH, WW>(p, rwc, j);
-          const float sc = half ? p.scale : 1.f;
-          bf16* dst = p.dqkv + static_cast<long long>(gk.row) * (3LL * p.C) + (half ? p.C : 2 * p.C) + head * HD;
+          const float sc = g ? p.scale : 1.f;
+          bf16* dst = p.dqkv + static_cast<long long>(gk.row) * (3LL * p.C) + (g ? p.C : 2 * p.C) + head * HD;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint4 w;
@@ -826,10 +812,14 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
             reinterpret_cast<uint4*>(dst)[c] = w;
           }
         }
-        const int qi = half * 128 + r;      // query row of the dQ block this thread reads
+      } else {
+        // dQ partial of this key half: bf16 red.add (REDG.BF16x8) into the zeroed Q block, needed back only at the
+        // next window's 8th sub-tile
+        const int mb = g - 2;
+        const int qi = mb * 128 + r;      // query row of the dQ block this thread reads
         tc::mbar_wait(unit_done, rn & 1);
         tc::fence_after_sync();
-        tc::tmem_ld_32x32b_x32(tmem_base + lane_addr + COL_DQ + half * 32, acc);
+        tc::tmem_ld_32x32b_x32(tmem_base + lane_addr + COL_DQ + mb * 32, acc);
         tc::tmem_ld_wait();
         tc::fence_before_sync();
         tc::mbar_arrive(dq_read);
@@ -844,34 +834,32 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
                            pack_bf16(__uint_as_float(acc[8 * c + 4]) * p.scale, __uint_as_float(acc[8 * c + 5]) * p.scale),
                            pack_bf16(__uint_as_float(acc[8 * c + 6]) * p.scale, __uint_as_float(acc[8 * c + 7]) * p.scale));
         }
+      }
     };
 
-    for (int T = g; T < TT; T += 2) {
+    for (int T = g; T < TT; T += NGRP) {
       const int n = T / NSUB, t = T % NSUB, st = n & 1;
       const int s = blockIdx.x + n * gridDim.x;
-      if (t < 2) {                                   // first sub-tile of this group in the window
+      if (t < NGRP) {                                // first sub-tile of this group in the window
         wc_prev = wc;
         wc = win_coord(p, s, WD, WH, WW);
         ck4 = static_cast<uint32_t>(token_geom_w<WD, WH, WW>(p, wc, jb).code) * 0x01010101u;
       }
       const uint8_t* sb = stages + st * BWD_STAGE_BYTES;
-      const int q0 = t * QS + half * 16;
+      const int q0 = t * QS;
 
-      tc_q = TCLK();
-      tc::mbar_wait(&s_full[g], (T >> 1) & 1);
+      tc::mbar_wait(&s_full[g], (T >> 2) & 1);
       tc::fence_after_sync();
-      tc_wait += TCLK() - tc_q; tc_q = TCLK();
       float x[16], dp[16];
+      const uint32_t buf = tmem_base + lane_addr + COL_BUF + g * 32;
       {
         uint32_t u0[16], u1[16];
-        const uint32_t base = tmem_base + lane_addr + COL_BUF + g * 64 + half * 16;
-        tc::tmem_ld_32x32b_x16(base, u0);
-        tc::tmem_ld_32x32b_x16(base + 32, u1);
+        tc::tmem_ld_32x32b_x16(buf, u0);
+        tc::tmem_ld_32x32b_x16(buf + 16, u1);
         tc::tmem_ld_wait();
 #pragma unroll
         for (int k = 0; k < 16; ++k) { x[k] = __uint_as_float(u0[k]); dp[k] = __uint_as_float(u1[k]); }
       }
-      tc_ld += TCLK() - tc_q; tc_q = TCLK();
       const int qr0 = q0 / WW;
       switch (q0 % WW) {
         case 0: add_bias_t16<WD, WH, WW, 0>(x, bias_s, rowbaseT, qr0, cscale); break;
@@ -906,13 +894,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
           dk[2 * c + 1] = pack_bf16(p2 * (dp[4 * c + 2] - dl.z), p3 * (dp[4 * c + 3] - dl.w));
         }
       }
-      tc_math += TCLK() - tc_q; tc_q = TCLK();
-      // P^T / dS^T over the first 8 of this thread's own 16 columns (bf16 pairs): TMEM A operands
-      const uint32_t pb = tmem_base + lane_addr + COL_BUF + g * 64 + half * 16;
-      tc::tmem_st_32x32b_x8(pb, pk);
-      tc::tmem_st_32x32b_x8(pb + 32, dk);
+      // P^T / dS^T over the first 8 of their own 16 columns (bf16 pairs): TMEM A operands
+      tc::tmem_st_32x32b_x8(buf, pk);
+      tc::tmem_st_32x32b_x8(buf + 16, dk);
       // dS^T copy for dQ; the previous window's dQ MMAs of this query block must be done with the tile
-      if ((t & 3) < 2) tc::mbar_wait(&ds_free[t >> 2], (n & 1) ^ 1);
+      if ((t & 7) < NGRP) tc::mbar_wait(&ds_free[t >> 3], (n & 1) ^ 1);
       {
         uint8_t* dst = ds_tile + (q0 >> 6) * 16384 + ds_row;
         const int c0 = (q0 & 63) >> 3;
@@ -923,18 +909,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
       tc::tmem_st_wait();
       tc::fence_before_sync();
       tc::mbar_arrive(&p_ready[g]);
-      tc_st += TCLK() - tc_q; tc_q = TCLK();
 
-      if (g == 1 && t == 1 && n > 0) {
-        readout(n - 1, wc_prev);
-        tc_ro += TCLK() - tc_q;
-      }
+      if (t == g && n > 0) readout(n - 1, wc_prev);
     }
-    if (g == 1 && n_units > 0) readout(n_units - 1, wc);
-    if (g_bwd_timing != nullptr && lane == 0 && q4 == 0 && half == 0) {
-      unsigned long long* o = g_bwd_timing + ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + 5 + g * 5;
-      o[0] = tc_wait; o[1] = tc_ld; o[2] = tc_math; o[3] = tc_st; o[4] = tc_ro;
-    }
+    if (n_units > 0) readout(n_units - 1, wc);
     // ---- CTA end: fold this CTA's dense bias gradient [128 keys x 256 queries] (TMEM) onto the
     // relative_position_bias_table: dT[rpi(i,j)] += dB[j][i], rpi(i,j) = lin(i) - lin(j) + off
     // (models/swin_transformer_3d.py:132-152,186-190).  Shared-memory fp32 atomics into a 1573-entry table, then
@@ -956,7 +934,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
       }
       tc::named_bar_sync(2, 512);
       const int lin_j = lin_s[jb];
-      const int slice = (g * 2 + half) * 64;
+      const int slice = g * 64;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         uint32_t acc[32];      // the TMEM load is warp-collective: never under a divergent branch
@@ -1038,29 +1016,7 @@ int wattn_tc_bwd(const WinAttnArgs& a, float* delta, cudaStream_t stream) {
   if (groups > a.S) groups = a.S;
   groups = ceil_div(a.S, ceil_div(a.S, groups));
   dim3 grid(groups, a.heads, 2);
-  static int timing = -1;
-  static unsigned long long* tbuf = nullptr;
-  if (timing < 0) {
-    const char* e = getenv("VSN_WATTN_TIMING");
-    timing = (e != nullptr && e[0] == '1') ? 1 : 0;
-    if (timing) {
-      VSN_CUDA(cudaMalloc(&tbuf, 1024 * 16 * 8));
-      VSN_CUDA(cudaMemcpyToSymbol(g_bwd_timing, &tbuf, sizeof(tbuf)));
-    }
-  }
   wattn_bwd_kernel<6, 7, 6><<<grid, BWD_THREADS, SM::TOTAL, stream>>>(a, delta);
   VSN_LAUNCH_CHECK();
-  if (timing) {
-    const int n = grid.x * grid.y * grid.z;
-    static unsigned long long host[1024 * 16];
-    VSN_CUDA(cudaStreamSynchronize(stream));
-    VSN_CUDA(cudaMemcpy(host, tbuf, n * 16 * 8, cudaMemcpyDeviceToHost));
-    double acc[16] = {0};
-    for (int i = 0; i < n; ++i) for (int k = 0; k < 16; ++k) acc[k] += static_cast<double>(host[i * 16 + k]) / n;
-    fprintf(stderr, "wattn_bwd timing (mean cycles per CTA over %d CTAs, %.0f sub-tiles): MMA warp total %.0f | wait ld_full %.0f "
-            "| wait p_ready %.0f | wait acc_read %.0f || group0: wait s_full %.0f ldtm %.0f math %.0f store+arrive %.0f || "
-            "group1: wait s_full %.0f ldtm %.0f math %.0f store+arrive %.0f readout %.0f\n", n, acc[4], acc[0], acc[1], acc[2], acc[3],
-            acc[5], acc[6], acc[7], acc[8], acc[10], acc[11], acc[12], acc[13], acc[14]);
-  }
   return 0;
 }
