@@ -82,6 +82,11 @@ def install_stubs():
             sys.modules[name] = types.ModuleType(name)
     sys.modules["nilearn"].image = sys.modules["nilearn.image"]
     sys.modules["nilearn"].masking = sys.modules["nilearn.masking"]
+
+    def _unavailable(*a, **kw):
+        raise RuntimeError("NIfTI preprocessing is not part of the harness (the .pt cache is synthetic)")
+    sys.modules["nilearn.image"].resample_img = _unavailable
+    sys.modules["nibabel"].load = _unavailable
     return ref_root
 
 
@@ -131,6 +136,47 @@ def write_config(out, ref_root, arch, img_size, steps, classes):
     return path
 
 
+def compare_checkpoint(out, arch, img):
+    """Load the checkpoint the trainer wrote (its "model" entry is the EMA state, train/train_transformer.py:808) into
+    the REFERENCE's own model class on the CPU and into the vsn_b200 drop-in on the GPU; same input, compare logits."""
+    import glob
+    import torch
+    ck = sorted(glob.glob(os.path.join(out, "runs", f"{arch}_harness", "*_last.pt")))
+    if not ck:
+        raise SystemExit("compare: no *_last.pt checkpoint")
+    ckpt = torch.load(ck[-1], map_location="cpu", weights_only=False)
+    sd = ckpt["model"]
+    from oracle import refshim
+    refshim.install()
+    if arch == "swin":
+        from models.swin_transformer_3d import SwinTransformerT as RefModel
+        kw = dict(in_channels=1, patch_size=[4, 4, 4], embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24],
+                  window_size=[6, 7, 6], mlp_ratio=4.0, qkv_bias=True, dropout=0.0, attention_dropout=0.0,
+                  stochastic_depth_prob=0.15, num_classes=3, norm_layer=torch.nn.LayerNorm)
+    else:
+        from models.vit_3d import ViTS as RefModel
+        kw = dict(img_size=tuple(img), num_classes=3, in_channels=1, patch_size=(16, 16, 16), mlp_ratio=4.0, dropout=0.0,
+                  attention_dropout=0.0, embed_dim=384, num_heads=6, depth=12)
+    ref = RefModel(**kw).eval()
+    missing, unexpected = ref.load_state_dict(sd, strict=True), None
+    refshim.uninstall()
+    import vsn_b200  # noqa: F401
+    from vsn_b200 import swin_model, vit_model
+    Ours = swin_model.SwinTransformerT if arch == "swin" else vit_model.ViTS
+    ours = Ours(**kw).cuda().eval()
+    ours.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 1, *img, generator=g).half().float()
+    with torch.no_grad():
+        zr = ref(x)
+        zo = ours(x.cuda()).cpu()
+    err = float((zo - zr).norm() / zr.norm())
+    print(f"compare: checkpoint {os.path.basename(ck[-1])} (step {ckpt.get('step')}), {len(sd)} tensors loaded strictly into "
+          f"the reference {RefModel.__name__} (CPU fp32) and the vsn_b200 drop-in (GPU): logits rel err {err:.3e}")
+    print("compare: reference logits", [round(float(v), 4) for v in zr[0]], "drop-in", [round(float(v), 4) for v in zo[0]])
+    assert err < 2e-2, err
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--arch", default="swin", choices=["swin", "vit"])
@@ -138,6 +184,8 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "trainer_harness"))
     ap.add_argument("--img-size", type=int, nargs=3, default=None)
     ap.add_argument("--resume", action="store_true", help="resume from the _last.pt checkpoint of a previous run")
+    ap.add_argument("--compare", action="store_true",
+                    help="no training: load the run's _last.pt into the reference model (CPU) and the drop-in (GPU)")
     ap.add_argument("--reference-models", action="store_true",
                     help="do NOT shadow the reference's modules (control run of the harness itself, any device)")
     a = ap.parse_args()
@@ -145,6 +193,8 @@ def main():
     os.makedirs(out, exist_ok=True)
     classes = ["CN", "AD", "FTD"]
     img = tuple(a.img_size) if a.img_size else ((48, 56, 48) if a.arch == "swin" else (48, 64, 48))
+    if a.compare:
+        return compare_checkpoint(out, a.arch, img)
     ref_root = install_stubs()
     rank = int(os.environ.get("RANK", "0"))
     if rank == 0:
