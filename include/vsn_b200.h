@@ -74,8 +74,10 @@ int vsn_colreduce(const void* dy, long long lddy, int dy_bf16, const float* x, l
  * win=0: dense sequences of N tokens (ViT-3D, models/vit_3d.py:129-141); geom/table NULL. */
 int vsn_attn_fwd(const void* qkv, void* out, float* lse, int S, int N, int heads, int hd, int win, const int* geom,
                  const float* table, int table_len, float scale, void* stream);
-/* delta [S, heads, ceil64(N)] and dbias_dense [heads, ceil64(N), ceil64(N)] (zeroed) are caller scratch;
- * dqkv [T, 3C] bf16 is fully written for every real token; dtable [table_len, heads] fp32 is accumulated. */
+/* delta [S, heads, ceil64(N)] and dbias_dense are caller scratch: dbias_dense is [heads, ceil64(N), ceil64(N)] fp32,
+ * zeroed, for windows the tcgen05 kernels do not cover; for win=0 with hd=64 (ViT-3D) it is the fp32 dQ accumulator
+ * [T, heads*hd] (any contents); NULL otherwise.  dqkv [T, 3C] bf16 is fully written for every real token;
+ * dtable [table_len, heads] fp32 is accumulated.  lse is whatever vsn_attn_fwd wrote for the same arguments. */
 int vsn_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
                  float* dbias_dense, float* dtable, int S, int N, int heads, int hd, int win, const int* geom,
                  const float* table, int table_len, float scale, void* stream);

@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include "wattn_tc.cuh"
+#include "dattn_tc.cuh"
 
 namespace {
 
@@ -710,6 +711,11 @@ extern "C" int vsn_attn_fwd(const void* qkv, void* out, float* lse, int S, int N
   dim3 grid(p.Npad / TQ, heads, S);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (win && wattn_tc_supported(p.wd, p.wh, p.ww, hd)) return wattn_tc_fwd(to_tc_args(p), st);
+  if (!win && dattn_tc_supported(hd)) {
+    DenseAttnArgs d = {};
+    d.qkv = p.qkv; d.out = p.out; d.lse = p.lse; d.S = S; d.N = N; d.Npad = p.Npad; d.heads = heads; d.C = p.C; d.scale = scale;
+    return dattn_tc_fwd(d, st);
+  }
 #define VSN_FWD(HD, WIN)                                                            \
   {                                                                                 \
     const size_t sm = 5 * Smem<HD>::TILE + extra_bytes<HD>(p, WIN, false);          \
@@ -746,6 +752,13 @@ extern "C" int vsn_attn_bwd(const void* qkv, const void* out, const void* dout, 
     WinAttnArgs ta = to_tc_args(p);
     ta.dtable = table != nullptr ? dtable : nullptr;
     return wattn_tc_bwd(ta, delta, st);
+  }
+  if (!win && dattn_tc_supported(hd)) {
+    // dense head_dim 64 (ViT-3D): tcgen05 kernels; `dbias_dense` is the fp32 dQ scratch [S*N, C] here
+    DenseAttnArgs d = {};
+    d.qkv = p.qkv; d.out = const_cast<bf16*>(o); d.lse = p.lse; d.dout = p.dout; d.dqkv = p.dqkv; d.delta = delta;
+    d.dq_acc = dbias_dense; d.S = S; d.N = N; d.Npad = p.Npad; d.heads = heads; d.C = p.C; d.scale = scale;
+    return dattn_tc_bwd(d, st);
   }
   if (win) attn_delta_kernel<true><<<S, 128, 0, st>>>(p, o, delta);
   else attn_delta_kernel<false><<<S, 128, 0, st>>>(p, o, delta);

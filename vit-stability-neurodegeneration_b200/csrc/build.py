@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB = os.path.join(PKG, "libvsn_b200.so")
-SOURCES = ["api.cu", "gemm_tc.cu", "attn.cu", "wattn_tc.cu", "norm.cu", "layout.cu", "optim.cu"]
+SOURCES = ["api.cu", "gemm_tc.cu", "attn.cu", "wattn_tc.cu", "dattn_tc.cu", "norm.cu", "layout.cu", "optim.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math" if False else "-DVSN_B200=1"]
 

@@ -666,6 +666,12 @@ int forced_ew() {
 
 }  // namespace
 
+// shared with the dense-attention kernels (dattn_tc.cu)
+int vsn_make_tmap_2d_bf16(CUtensorMap* map, const void* base, long long dim0, long long dim1, long long ld, int box0,
+                          int box1) {
+  return make_tmap_2d(map, base, dim0, dim1, ld, box0, box1);
+}
+
 extern "C" int vsn_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, int M,
                              int N, int K, void* out, long long ldo, int out_kind, const float* bias, int act,
                              void* aux, long long ldaux, const float* resid, long long ldr, const float* row_scale,

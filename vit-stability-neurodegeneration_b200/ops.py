@@ -184,7 +184,11 @@ def attn_bwd(qkv, out, dout, lse, heads: int, hd: int, *, S: int, N: int, scale:
     assert dout.dtype == BF16 and dout.is_contiguous()
     delta = torch.empty((S, heads, npad), device=qkv.device, dtype=F32)
     tc_path = geom is not None and hd == 32 and tuple(geom.window) == (6, 7, 6)   # folds the table gradient in-kernel
-    dense = torch.zeros((heads, npad, npad), device=qkv.device, dtype=F32) if (table is not None and not tc_path) else None
+    if geom is None and hd == 64:
+        # dense tcgen05 path (ViT-3D): the scratch argument is the fp32 dQ accumulator [T, C] (zeroed by the library)
+        dense = torch.empty((T, heads * hd), device=qkv.device, dtype=F32)
+    else:
+        dense = torch.zeros((heads, npad, npad), device=qkv.device, dtype=F32) if (table is not None and not tc_path) else None
     # real tokens are all written by the kernels; padded-grid tokens always belong to a window too
     dqkv = torch.empty_like(qkv)
     if _lib.PROFILE is not None:
