@@ -55,6 +55,8 @@ def parse(argv=None):
     ap.add_argument("--mixup", action="store_true", help="MixUp the volumes and labels on the device every step")
     ap.add_argument("--no-ema", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of graph replay")
+    ap.add_argument("--no-graph-comm", action="store_true",
+                    help="N>1, graph mode: reduce the buckets after the last replay instead of inside the graph")
     ap.add_argument("--torch-ddp", action="store_true", help="N>1: use torch DDP instead of vsn_b200.ddp.GradAllReduce")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the instrumented pass (roofline = null)")
@@ -474,7 +476,8 @@ class CudaBackend:
                 from vsn_b200.ddp import GradAllReduce
                 sync = GradAllReduce(model.parameters(), bucket_mb=25.0, buffers=model.buffers())
         graph = not args.no_graph and ddp is None
-        ts = TrainStep(model, use_sam=args.sam, use_ema=not args.no_ema, ddp_model=ddp, grad_sync=sync, graph=graph)
+        ts = TrainStep(model, use_sam=args.sam, use_ema=not args.no_ema, ddp_model=ddp, grad_sync=sync, graph=graph,
+                       graph_comm=not args.no_graph_comm)
         G = args.micro_batches
         vol = VOLUMES[args.model]
         host = [synth_batch(args.batch, args.classes, seed=1234 + self.rank * 100 + i, volume=vol) for i in range(G)]

@@ -50,12 +50,16 @@ class TrainStep:
     grad_sync   a `ddp.GradAllReduce` over `model.parameters()` built by the caller (N > 1); without one the step
                 builds its own arena (world size 1: nothing is exchanged)
     graph       capture forward + loss + backward of a micro-batch in a CUDA graph and replay it
+    graph_comm  (N > 1, graph mode) capture a second graph for the LAST micro-batch of a pass with the bucket
+                all-reduces inside it: NCCL runs on the communication stream as a forked branch of the graph, each
+                bucket as soon as backward has completed it, so the exchange overlaps the rest of backward exactly as
+                in the eager loop.  Off: the buckets are reduced after the last replay (exposed, ~0.5 ms for 117 MB).
     """
 
     def __init__(self, model: torch.nn.Module, *, lr: float = 1e-4, weight_decay: float = 0.05, use_sam: bool = False,
                  sam_rho: float = 0.05, use_ema: bool = True, ema_decay: float = 0.999, smoothing: float = 0.1,
                  ddp_model: Optional[torch.nn.Module] = None, grad_sync: Optional[GradAllReduce] = None,
-                 graph: bool = False):
+                 graph: bool = False, graph_comm: bool = True):
         self.module = model                       # the bare module (EMA / parameters)
         self.model = ddp_model if ddp_model is not None else model   # what forward is called on
         self.autograd_grads = ddp_model is not None
@@ -75,7 +79,9 @@ class TrainStep:
         self.ema = EMAModel(model=model, decay=ema_decay) if use_ema else None
         self.smoothing = smoothing
         self.use_graph = graph
+        self.graph_comm = graph_comm
         self._graph = None            # (torch.cuda.CUDAGraph, static x, static y, static loss)
+        self._graph_sync = None       # same micro-batch with the bucket all-reduces captured inside (last micro-batch)
         self._graph_key = None
         self.graph_kernel_nodes = 0
         self.graph_replays = 0
@@ -88,7 +94,10 @@ class TrainStep:
         return loss.detach()
 
     def _capture(self, x: torch.Tensor, y: torch.Tensor, n: int) -> None:
-        """Warm up on a side stream (allocator, plans, lazily built tables), then capture one micro-batch."""
+        """Warm up on a side stream (allocator, plans, lazily built tables), then capture one micro-batch; with
+        several ranks and `graph_comm`, capture it a second time with the gradient exchange inside."""
+        from . import _lib
+        gs = self.grad_sync
         sx, sy = torch.empty_like(x), torch.empty_like(y)
         sx.copy_(x)
         sy.copy_(y)
@@ -98,14 +107,31 @@ class TrainStep:
             for _ in range(2):
                 self._fwd_bwd(sx, sy, n)
         torch.cuda.current_stream().wait_stream(side)
-        from . import _lib
         g = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
         with torch.cuda.graph(g):
             sl = self._fwd_bwd(sx, sy, n)
         self.graph_kernel_nodes = _lib.launch_count() - n0     # library kernels one replay launches
-        self.grad_sync.zero_grad()                 # warm-up and capture passes left their sums in the arena
         self._graph = (g, sx, sy, sl)
+        self._graph_sync = None
+        if gs.world > 1 and self.graph_comm:
+            notify = lambda grads: [gs.mark_ready(t) for t in grads]     # noqa: E731
+            GradSink.notify = notify
+            try:
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):                  # eager rehearsal with the collectives (every rank)
+                    self._fwd_bwd(sx, sy, n)
+                    gs.finish()
+                torch.cuda.current_stream().wait_stream(side)
+                g2 = torch.cuda.CUDAGraph()
+                # the NCCL watchdog thread queries events while we capture: keep the capture thread-local
+                with torch.cuda.graph(g2, pool=g.pool(), capture_error_mode="thread_local"):
+                    sl2 = self._fwd_bwd(sx, sy, n)
+                    gs.finish()                                # joins the communication stream back into the graph
+                self._graph_sync = (g2, sx, sy, sl2)
+            finally:
+                GradSink.notify = None
+        gs.zero_grad()                             # warm-up and capture passes left their sums in the arena
         self._graph_key = (tuple(x.shape), x.dtype, tuple(y.shape), y.dtype, n)
 
     def _refresh_weights(self) -> None:
@@ -140,8 +166,8 @@ class TrainStep:
                         raise ValueError("graph mode needs micro-batches of one shape and dtype")
                 if self._graph is None or self._graph_key != key:
                     self._capture(x0, y0, n)       # before anything of this pass has been accumulated
-                g, sx, sy, sl = self._graph
-                for x, y in batches:
+                for i, (x, y) in enumerate(batches):
+                    g, sx, sy, sl = self._graph_sync if (i == n - 1 and self._graph_sync is not None) else self._graph
                     if x.data_ptr() != sx.data_ptr():
                         sx.copy_(x, non_blocking=True)
                     if y.data_ptr() != sy.data_ptr():
@@ -149,7 +175,8 @@ class TrainStep:
                     g.replay()
                     self.graph_replays += 1
                     total = sl.clone() if total is None else total + sl
-                gs.reduce_all()
+                if self._graph_sync is None:
+                    gs.reduce_all()               # no collectives in the graph: reduce now (exposed)
             else:
                 for i, (x, y) in enumerate(batches):
                     last = i == n - 1
