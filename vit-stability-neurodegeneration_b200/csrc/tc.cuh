@@ -26,6 +26,14 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// One arrival for a whole (converged) warp: every lane has made its own writes visible (tcgen05.wait::st +
+// tcgen05.fence::before_thread_sync, fence.proxy.async for smem the tensor core reads), __syncwarp orders them before
+// lane 0's releasing arrive.  Arrivals on one mbarrier are serialised shared-memory atomics: 256 per hand-over cost
+// ~800 clk in the attention backward's pipeline skeleton (profiles/r2_wattn_bwd_notes.md), 8 cost nothing.
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
 // One probe of the phase.  With a suspend-time hint the hardware may keep the thread asleep up to that many
 // nanoseconds (it is woken by the arrival that completes the phase), so a waiting warp re-issues the probe loop far
 // less often: in the attention kernels a third of all issued instructions were such probes (BRA / SYNCS / YIELD),
