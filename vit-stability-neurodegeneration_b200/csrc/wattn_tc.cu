@@ -509,12 +509,14 @@ int wattn_tc_fwd(const WinAttnArgs& a, cudaStream_t stream) {
 constexpr int BWD_THREADS = 20 * 32;           // 16 compute warps + one warpgroup of helpers (loader, MMA issuer, two idle)
 constexpr int QS = 32;                         // queries per sub-tile
 constexpr int NSUB = NP / QS;                  // 8
-constexpr int BWD_STAGE_BYTES = 51712;         // Q 16K | dO 16K | K_half 8K | V_half 8K | lse2 1K | delta 1K | qcode 256
+// stage: Q 16K | dO 16K | K_half 8K | V_half 8K | lse2 1K | delta 1K | region code 256 | source row 1K | masked flag
+constexpr int BWD_OFF_CODE = 51200, BWD_OFF_ROW = 51456, BWD_OFF_FLAG = 52480;
+constexpr int BWD_STAGE_BYTES = 52736;         // 2 stages = 103 KB (1024-aligned for the dS tile behind them)
 constexpr int DS_TILE_BYTES = 128 * NP * 2;    // 64 KB: dS^T as MN-major A operand, 128B swizzle
 
 template <int WD, int WH, int WW>
 struct BwdSmem {
-  static constexpr int DS = 2 * BWD_STAGE_BYTES;                    // 103424 (1024-aligned)
+  static constexpr int DS = 2 * BWD_STAGE_BYTES;                    // 105472 (1024-aligned)
   static constexpr int BIAS = DS + DS_TILE_BYTES;
   static constexpr int IDENT = BIAS + ((BiasTab<WD, WH, WW>::BYTES + 1023) / 1024) * 1024;
   static constexpr int BARS = IDENT + 1024;
@@ -661,9 +663,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
       tc::mbar_wait_relaxed(&ld_empty[st], ((n >> 1) & 1) ^ 1);
       uint8_t* sb = stages + st * BWD_STAGE_BYTES;
       const WinCoord wc = win_coord(p, s, WD, WH, WW);
+      // the window's geometry is published with the tiles: the compute threads do no index math (their per-window
+      // win_coord + token_geom divisions were ~550 clk per sub-tile and group, profiles/r2_wattn_bwd_notes.md)
+      if (lane == 0) *reinterpret_cast<int*>(sb + BWD_OFF_FLAG) = wc.masked() ? 1 : 0;
       for (int i = lane; i < N; i += 32) {
         const TokenGeom g = token_geom_w<WD, WH, WW>(p, wc, i);
-        sb[51200 + i] = static_cast<uint8_t>(g.code);
+        sb[BWD_OFF_CODE + i] = static_cast<uint8_t>(g.code);
+        reinterpret_cast<int*>(sb + BWD_OFF_ROW)[i] = g.row;
         const bf16* src = p.qkv + g.row * ld + head * HD;
         const bf16* dsrc = p.dout + static_cast<long long>(g.row) * p.C + head * HD;
         const int kr = i - kh * 128;
@@ -794,14 +800,15 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
     }
     // smem dS tile: element (query q, key r) at (q/64)*16384 + (r/8)*1024 + (r%8)*128 + (((q%64)/8) ^ (r%8))*16
     const uint32_t ds_row = (r >> 3) * 1024 + (r & 7) * 128;
-    WinCoord wc = {};
+    bool masked = false;
     uint32_t ck4 = 0;
     long long tc_wait = 0, tc_ld = 0, tc_math = 0, tc_st = 0, tc_ro = 0, tc_q;
-    WinCoord wc_prev = {};
+    // source rows of this thread's key and of the query row it reads out (group 1), current and previous window
+    int krow = 0, qrow = 0, krow_prev = 0, qrow_prev = 0;
 
     // Read-out of window rn (group 1 only), run one sub-tile into the NEXT window so that kv_done / unit_done have
     // long fired and nothing here waits.
-    auto readout = [&](int rn, const WinCoord& rwc) {
+    auto readout = [&](int rn, int rk, int rq) {
         // ---- window read-out.  dV / dK rows of this key half: direct stores, released as soon as they are in
         // registers (the next window's first MMA overwrites them); dQ partial: bf16 red.add (REDG.BF16x8) into the
         // zeroed Q block, needed back only at the next window's 4th sub-tile.
@@ -813,9 +820,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
         tc::fence_before_sync();
         tc::mbar_arrive(acc_read);
         if (j < N) {
-          const TokenGeom gk = token_geom_w<WD, WH, WW>(p, rwc, j);
           const float sc = half ? p.scale : 1.f;
-          bf16* dst = p.dqkv + static_cast<long long>(gk.row) * (3LL * p.C) + (half ? p.C : 2 * p.C) + head * HD;
+          bf16* dst = p.dqkv + static_cast<long long>(rk) * (3LL * p.C) + (half ? p.C : 2 * p.C) + head * HD;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint4 w;
@@ -834,8 +840,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
         tc::fence_before_sync();
         tc::mbar_arrive(dq_read);
         if (qi < N) {
-          const TokenGeom gq = token_geom_w<WD, WH, WW>(p, rwc, qi);
-          bf16* dst = p.dqkv + static_cast<long long>(gq.row) * (3LL * p.C) + head * HD;
+          bf16* dst = p.dqkv + static_cast<long long>(rq) * (3LL * p.C) + head * HD;
 #pragma unroll
           for (int c = 0; c < 4; ++c)
             red_add_bf16x8(dst + 8 * c,
@@ -848,12 +853,6 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
 
     for (int T = g; T < TT; T += 2) {
       const int n = T / NSUB, t = T % NSUB, st = n & 1;
-      const int s = blockIdx.x + n * gridDim.x;
-      if (t < 2) {                                   // first sub-tile of this group in the window
-        wc_prev = wc;
-        wc = win_coord(p, s, WD, WH, WW);
-        ck4 = static_cast<uint32_t>(token_geom_w<WD, WH, WW>(p, wc, jb).code) * 0x01010101u;
-      }
       const uint8_t* sb = stages + st * BWD_STAGE_BYTES;
       const int q0 = t * QS + half * 16;
 
@@ -861,6 +860,15 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
       tc::mbar_wait(&s_full[g], (T >> 1) & 1);
       tc::fence_after_sync();
       tc_wait += TCLK() - tc_q; tc_q = TCLK();
+      if (t < 2) {                                   // first sub-tile of this group in the window: the loader's geometry
+        masked = *reinterpret_cast<const int*>(sb + BWD_OFF_FLAG) != 0;      // (s_full implies the stage's ld_full)
+        ck4 = static_cast<uint32_t>(sb[BWD_OFF_CODE + jb]) * 0x01010101u;
+        if (g == 1) {
+          krow_prev = krow; qrow_prev = qrow;
+          krow = reinterpret_cast<const int*>(sb + BWD_OFF_ROW)[jb];
+          qrow = reinterpret_cast<const int*>(sb + BWD_OFF_ROW)[min(half * 128 + r, N - 1)];
+        }
+      }
       float x[16], dp[16];
       {
         uint32_t u0[16], u1[16];
@@ -878,8 +886,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
         case 2: add_bias_t16<WD, WH, WW, 2>(x, bias_s, rowbaseT, qr0, cscale); break;
         default: add_bias_t16<WD, WH, WW, 4>(x, bias_s, rowbaseT, qr0, cscale); break;
       }
-      if (wc.masked()) {
-        const uint4 qc = *reinterpret_cast<const uint4*>(sb + 51200 + q0);
+      if (masked) {
+        const uint4 qc = *reinterpret_cast<const uint4*>(sb + BWD_OFF_CODE + q0);
         const uint32_t qw[4] = {qc.x, qc.y, qc.z, qc.w};
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
@@ -926,11 +934,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
       tc_st += TCLK() - tc_q; tc_q = TCLK();
 
       if (g == 1 && t == 1 && n > 0) {
-        readout(n - 1, wc_prev);
+        readout(n - 1, krow_prev, qrow_prev);
         tc_ro += TCLK() - tc_q;
       }
     }
-    if (g == 1 && n_units > 0) readout(n_units - 1, wc);
+    if (g == 1 && n_units > 0) readout(n_units - 1, krow, qrow);
     if (g_bwd_timing != nullptr && lane == 0 && q4 == 0 && half == 0) {
       unsigned long long* o = g_bwd_timing + ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + 5 + g * 5;
       o[0] = tc_wait; o[1] = tc_ld; o[2] = tc_math; o[3] = tc_st; o[4] = tc_ro;
