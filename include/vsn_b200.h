@@ -138,6 +138,19 @@ int vsn_mt_ema(const long long* p_ptrs, const long long* new_ptrs, const long lo
                const long long* ema_ptrs, const long long* sizes, const int* chunk_tensor, const long long* chunk_off,
                int n_chunks, float w0, float w1, float w2, void* stream);
 
+/* AdamW over all parameter tensors in one pass, replacing torch.optim.AdamW(...).step() + optimizer.zero_grad() of
+ * train/train_transformer.py:2125-2147,1225-1260 and the GradScaler's unscale_/found_inf skip (:1203-1232) without a
+ * host synchronisation.  vsn_adamw_prepare: step += 1 unless *found_inf (nullable) != 0; ctl4 = {1 - beta1^step,
+ * sqrt(1 - beta2^step), skip, *inv_scale (nullable: 1)}.  vsn_mt_adamw: g *= inv_scale; p *= 1 - lr*weight_decay[t];
+ * m += (g - m)(1 - beta1); v = beta2 v + (1 - beta2) g^2 (1 - beta passed in, rounded from double as torch does); p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps); g = 0 if
+ * zero_grad.  Nothing is touched when ctl4[2] != 0. */
+int vsn_adamw_prepare(float* step, const float* found_inf, const float* inv_scale, float beta1, float beta2, float* ctl4,
+                      void* stream);
+int vsn_mt_adamw(const long long* p_ptrs, const long long* g_ptrs, const long long* m_ptrs, const long long* v_ptrs,
+                 const long long* sizes, const int* chunk_tensor, const long long* chunk_off, int n_chunks,
+                 const float* weight_decay, const float* ctl4, float lr, float beta2, float one_minus_beta1,
+                 float one_minus_beta2, float eps, int zero_grad, void* stream);
+
 /* dst_bf16[t] = bf16(src_fp32[t]): refreshes the bf16 copies of the GEMM weights once per forward. */
 int vsn_mt_cast_bf16(const long long* src_ptrs, const long long* dst_ptrs, const long long* sizes,
                      const int* chunk_tensor, const long long* chunk_off, int n_chunks, void* stream);

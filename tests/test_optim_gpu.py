@@ -155,3 +155,117 @@ def test_ema_ring_matches_reference_and_apply_restore_round_trip():
     for k in keys:
         assert torch.equal(net.state_dict()[k], before[k]), k
     assert ema.orig_state is None
+
+
+# ----------------------------------------------------------------------------- fused AdamW
+def _adamw_pair(optim, sizes=((384, 96), (96,), (1573, 3), (7,), (3, 768)), seed=0):
+    gen = torch.Generator().manual_seed(seed)
+    a = [torch.nn.Parameter(torch.randn(*s, generator=gen).cuda()) for s in sizes]
+    b = [torch.nn.Parameter(p.detach().clone()) for p in a]
+    mk = lambda ps: [{"params": [ps[0], ps[2], ps[4]]}, {"params": [ps[1], ps[3]], "weight_decay": 0.0}]   # noqa: E731
+    ref = torch.optim.AdamW(mk(a), lr=3e-3, weight_decay=0.05, foreach=False, fused=False)
+    ours = optim.FusedAdamW(mk(b), lr=3e-3, weight_decay=0.05, fused=True)
+    return a, b, ref, ours, gen
+
+
+def test_fused_adamw_matches_torch_adamw_and_clears_gradients():
+    """train/train_transformer.py:2125-2147: torch.optim.AdamW's update, five steps, two parameter groups, sizes with
+    unaligned tails, a changing learning rate; `step(zero_grad=True)` leaves zeroed gradients in place."""
+    optim = _optim()
+    a, b, ref, ours, gen = _adamw_pair(optim)
+    for it in range(5):
+        for grp_r, grp_o in zip(ref.param_groups, ours.param_groups):
+            grp_r["lr"] = grp_o["lr"] = 3e-3 * (1.0 - 0.1 * it)                     # a scheduler at work
+        for p, q in zip(a, b):
+            g = torch.randn(p.shape, generator=gen).cuda() * (10.0 if it == 2 else 1.0)
+            p.grad, q.grad = g.clone(), g.clone()
+        ref.step()
+        ours.step(zero_grad=True)
+        for p, q in zip(a, b):
+            _close(q, p.detach().cpu().numpy(), rtol=2e-6, atol=1e-7)
+            assert q.grad is not None and float(q.grad.abs().max()) == 0.0
+    for p, q in zip(a, b):
+        _close(ours.state[q]["exp_avg"], ref.state[p]["exp_avg"].cpu().numpy(), rtol=2e-6, atol=2e-7)   # |m| ~ 1: fma order
+        _close(ours.state[q]["exp_avg_sq"], ref.state[p]["exp_avg_sq"].cpu().numpy(), rtol=5e-6, atol=1e-9)
+
+
+def test_fused_adamw_state_dict_interchanges_with_torch_adamw():
+    """Checkpoints written by the reference trainer (train/train_transformer.py:752-820) load into FusedAdamW and back."""
+    optim = _optim()
+    a, b, ref, ours, gen = _adamw_pair(optim, seed=1)
+    for it in range(2):
+        for p, q in zip(a, b):
+            g = torch.randn(p.shape, generator=gen).cuda()
+            p.grad, q.grad = g.clone(), g.clone()
+        ref.step()
+        ours.step()
+    sd_ours, sd_ref = ours.state_dict(), ref.state_dict()
+    assert sd_ours["state"].keys() == sd_ref["state"].keys()
+    for k in sd_ref["state"]:
+        assert set(sd_ours["state"][k]) == set(sd_ref["state"][k]) == {"step", "exp_avg", "exp_avg_sq"}
+        assert float(sd_ours["state"][k]["step"]) == float(sd_ref["state"][k]["step"]) == 2.0
+    # swap the states and continue: both must stay on the same trajectory
+    ours.load_state_dict(sd_ref)
+    ref.load_state_dict(sd_ours)
+    for p, q in zip(a, b):
+        g = torch.randn(p.shape, generator=gen).cuda()
+        p.grad, q.grad = g.clone(), g.clone()
+    ref.step()
+    ours.step()
+    for p, q in zip(a, b):
+        _close(q, p.detach().cpu().numpy(), rtol=2e-6, atol=1e-7)
+    assert float(ours.state_dict()["state"][0]["step"]) == 3.0
+
+
+def test_fused_adamw_under_grad_scaler_unscales_and_skips_on_inf():
+    """GradScaler.step hands grad_scale / found_inf to the optimizer as device tensors (:1203-1232): the kernel
+    unscales in the same pass, and an overflow skips the update AND the step count without a host round trip."""
+    optim = _optim()
+    a, b, ref, ours, gen = _adamw_pair(optim, seed=2)
+    sc_r = torch.amp.GradScaler("cuda", init_scale=1024.0)
+    sc_o = torch.amp.GradScaler("cuda", init_scale=1024.0)
+    one = torch.ones((), device="cuda")
+    sc_r.scale(one), sc_o.scale(one)                       # the scale tensor is created lazily by the first scale()
+    for it in range(4):
+        for p, q in zip(a, b):
+            g = torch.randn(p.shape, generator=gen).cuda() * 1024.0 * (0.5 ** sum(1 for j in (1,) if j < it))
+            if it == 1:
+                g.view(-1)[0] = float("inf")
+            p.grad, q.grad = g.clone(), g.clone()
+        sc_r.step(ref)
+        sc_r.update()
+        sc_o.step(ours)
+        sc_o.update()
+        assert sc_r.get_scale() == sc_o.get_scale()
+        for p, q in zip(a, b):
+            _close(q, p.detach().cpu().numpy(), rtol=2e-6, atol=1e-7)
+    assert float(ours.state_dict()["state"][0]["step"]) == 3.0      # four calls, one skipped
+
+
+def test_train_step_fused_adamw_equals_torch_adamw():
+    """TrainStep with optim.FusedAdamW and with torch.optim.AdamW(fused=True) walks the same weights (tiny Swin, SAM off
+    and on, two micro-batches)."""
+    import vsn_b200  # noqa: F401
+    from vsn_b200 import swin_model, train
+    from oracle import cases
+    case = cases.SWIN_CASES["swin_small_even"]
+    for use_sam in (False, True):
+        finals = []
+        for fused in (True, False):
+            torch.manual_seed(0)
+            m = swin_model.SwinTransformer(**cases.swin_ctor_kwargs(case)).cuda()
+            init = [p.detach().clone() for p in m.parameters()]
+            ts = train.TrainStep(m, lr=1e-3, use_sam=use_sam, use_ema=False, fused_adamw=fused)
+            g = torch.Generator().manual_seed(5)
+            for _ in range(2):
+                batches = [(torch.randn(*case["input"], generator=g).cuda().half(),
+                            torch.softmax(torch.randn(case["input"][0], case["num_classes"], generator=g), -1).cuda())
+                           for _ in range(2)]
+                ts.step(batches)
+            finals.append([p.detach() - p0 for p, p0 in zip(m.parameters(), init)])
+        # the gradient kernels accumulate with atomics (summation order varies run to run), and AdamW turns a sign flip
+        # of a noise-level gradient into a full +-lr move: compare the UPDATES in the L2 sense
+        num = sum(float(((x - y) ** 2).sum()) for x, y in zip(*finals))
+        den = sum(float((y ** 2).sum()) for y in finals[1])
+        # (measured 1.9e-3: a weight that differs in its last fp32 bit can round to the other bf16 neighbour for step 2)
+        assert den > 0 and (num / den) ** 0.5 < 1e-2, (use_sam, (num / den) ** 0.5)

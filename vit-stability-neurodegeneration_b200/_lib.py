@@ -39,6 +39,8 @@ SIGNATURES = {
     "vsn_mt_sam_perturb": [_p, _p, _p, _p, _p, _p, _i, _p, _p, _i, _p],
     "vsn_mt_copy": [_p, _p, _p, _p, _p, _i, _p],
     "vsn_mt_cast_bf16": [_p, _p, _p, _p, _p, _i, _p],
+    "vsn_adamw_prepare": [_p, _p, _p, _f, _f, _p, _p],
+    "vsn_mt_adamw": [_p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _f, _f, _f, _f, _f, _i, _p],
     "vsn_mt_ema": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _f, _f, _f, _p],
 }
 

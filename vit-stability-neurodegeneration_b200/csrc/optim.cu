@@ -202,6 +202,68 @@ __global__ void __launch_bounds__(MT_THREADS) mt_ema_kernel(const long long* p_p
   }
 }
 
+// AdamW over every parameter tensor in ONE pass (torch.optim.AdamW, train/train_transformer.py:2125-2147):
+//   g' = g * inv_scale;  p *= 1 - lr*wd[t];  m += (g' - m)(1 - b1);  v = b2 v + (1 - b2) g'^2;
+//   p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps);   optionally g = 0 (the next pass accumulates into it).
+// ctl = { bc1, sqrt(bc2), skip, inv_scale } comes from adamw_prepare_kernel: the step count, the GradScaler's
+// found_inf / inv_scale live on the device, so a skipped step costs no host synchronisation.
+// 28 B read+written per parameter (p, g, m, v in; p, m, v out) + 4 B for the fused gradient clear.
+__global__ void __launch_bounds__(MT_THREADS) mt_adamw_kernel(const long long* p_ptrs, const long long* g_ptrs,
+                                                              const long long* m_ptrs, const long long* v_ptrs,
+                                                              MTTable tab, const float* __restrict__ wd,
+                                                              const float* __restrict__ ctl, float lr, float b2, float omb1,
+                                                              float omb2, float eps, int zero_grad) {
+  int tensor; long long off, n;
+  if (!chunk_span(tab, tensor, off, n)) return;
+  const float bc1 = ctl[0], bc2s = ctl[1], inv_scale = ctl[3];
+  if (ctl[2] != 0.f) return;                              // found_inf: the whole step is skipped (gradients kept)
+  float* p = reinterpret_cast<float*>(p_ptrs[tensor]) + off;
+  float* g = reinterpret_cast<float*>(g_ptrs[tensor]) + off;
+  float* m = reinterpret_cast<float*>(m_ptrs[tensor]) + off;
+  float* v = reinterpret_cast<float*>(v_ptrs[tensor]) + off;
+  const float decay = 1.f - lr * wd[tensor], step_size = lr / bc1;   // omb1/omb2 = 1 - beta, rounded from double like torch's
+  auto upd = [&](float& pw, float gw, float& mw, float& vw) {
+    gw *= inv_scale;
+    pw *= decay;
+    mw = fmaf(gw - mw, omb1, mw);
+    vw = fmaf(omb2 * gw, gw, b2 * vw);
+    pw = pw - step_size * (mw / (sqrtf(vw) / bc2s + eps));
+  };
+  long long done = 0;
+  if (aligned16(p, g, m, v)) {
+    const long long n4 = n >> 2;
+#pragma unroll 2
+    for (long long i = threadIdx.x; i < n4; i += MT_THREADS) {
+      float4 pw = reinterpret_cast<float4*>(p)[i], mw = reinterpret_cast<float4*>(m)[i], vw = reinterpret_cast<float4*>(v)[i];
+      const float4 gw = reinterpret_cast<const float4*>(g)[i];
+      upd(pw.x, gw.x, mw.x, vw.x); upd(pw.y, gw.y, mw.y, vw.y); upd(pw.z, gw.z, mw.z, vw.z); upd(pw.w, gw.w, mw.w, vw.w);
+      reinterpret_cast<float4*>(p)[i] = pw;
+      reinterpret_cast<float4*>(m)[i] = mw;
+      reinterpret_cast<float4*>(v)[i] = vw;
+      if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    done = n4 << 2;
+  }
+  for (long long i = done + threadIdx.x; i < n; i += MT_THREADS) {
+    float pw = p[i], mw = m[i], vw = v[i];
+    upd(pw, g[i], mw, vw);
+    p[i] = pw; m[i] = mw; v[i] = vw;
+    if (zero_grad) g[i] = 0.f;
+  }
+}
+
+// step += 1 unless found_inf; ctl = { 1 - b1^step, sqrt(1 - b2^step), skip, inv_scale }
+__global__ void adamw_prepare_kernel(float* step, const float* found_inf, const float* inv_scale, float b1, float b2,
+                                     float* ctl) {
+  const bool skip = found_inf != nullptr && found_inf[0] != 0.f;
+  float s = step[0];
+  if (!skip) { s += 1.f; step[0] = s; }
+  ctl[0] = 1.f - powf(b1, s);
+  ctl[1] = sqrtf(1.f - powf(b2, s));
+  ctl[2] = skip ? 1.f : 0.f;
+  ctl[3] = inv_scale != nullptr ? inv_scale[0] : 1.f;
+}
+
 // dst_bf16 = bf16(src_fp32) per tensor: the bf16 shadow of the GEMM weights
 __global__ void __launch_bounds__(MT_THREADS) mt_cast_bf16_kernel(const long long* src_ptrs, const long long* dst_ptrs,
                                                                   MTTable tab) {
@@ -281,6 +343,26 @@ extern "C" int vsn_mt_ema(const long long* p_ptrs, const long long* new_ptrs, co
   MTTable t{sizes, chunk_tensor, chunk_off};
   mt_ema_kernel<<<n_chunks, MT_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p_ptrs, new_ptrs, s0_ptrs, s1_ptrs,
                                                                                      ema_ptrs, t, w0, w1, w2);
+  VSN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vsn_adamw_prepare(float* step, const float* found_inf, const float* inv_scale, float beta1, float beta2,
+                                 float* ctl4, void* stream) {
+  adamw_prepare_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(step, found_inf, inv_scale, beta1, beta2, ctl4);
+  VSN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vsn_mt_adamw(const long long* p_ptrs, const long long* g_ptrs, const long long* m_ptrs,
+                            const long long* v_ptrs, const long long* sizes, const int* chunk_tensor,
+                            const long long* chunk_off, int n_chunks, const float* weight_decay, const float* ctl4,
+                            float lr, float beta2, float one_minus_beta1, float one_minus_beta2, float eps,
+                            int zero_grad, void* stream) {
+  if (n_chunks == 0) return 0;
+  MTTable t{sizes, chunk_tensor, chunk_off};
+  mt_adamw_kernel<<<n_chunks, MT_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      p_ptrs, g_ptrs, m_ptrs, v_ptrs, t, weight_decay, ctl4, lr, beta2, one_minus_beta1, one_minus_beta2, eps, zero_grad);
   VSN_LAUNCH_CHECK();
   return 0;
 }

@@ -1,4 +1,4 @@
-"""SAM and EMA on top of the multi-tensor kernels (csrc/optim.cu).
+"""SAM, EMA and the fused AdamW on top of the multi-tensor kernels (csrc/optim.cu).
 
 `SAM` and `EMAModel` keep the constructor / method surface of the reference's
 `regularization/sam.py` and `utils/ema.py`, so `train/train_transformer.py` drives them unchanged; the
@@ -99,12 +99,147 @@ class MultiTensorTable:
         self._work(1, 6.0)               # read fp32, write bf16
         _lib.call("vsn_mt_cast_bf16", src_ptrs.data_ptr(), dst_ptrs.data_ptr(), *self._tab(), self._stream())
 
+    def adamw(self, p_ptrs, g_ptrs, m_ptrs, v_ptrs, wd, ctl, lr, beta1, beta2, eps, zero_grad):
+        self._work(7 + int(zero_grad))   # read p, g, m, v; write p, m, v (+ the cleared gradient): 28-32 B per parameter
+        _lib.call("vsn_mt_adamw", p_ptrs.data_ptr(), g_ptrs.data_ptr(), m_ptrs.data_ptr(), v_ptrs.data_ptr(),
+                  *self._tab(), wd.data_ptr(), ctl.data_ptr(), float(lr), float(beta2), 1.0 - float(beta1),
+                  1.0 - float(beta2), float(eps), int(zero_grad), self._stream())
+
     def ema(self, p_ptrs, new_ptrs, s0_ptrs, s1_ptrs, ema_ptrs, w0, w1, w2):
         self._work(3 + (s0_ptrs is not None) + (s1_ptrs is not None))   # read p (+s0, s1); write the new slot and the average
         _lib.call("vsn_mt_ema", p_ptrs.data_ptr(), new_ptrs.data_ptr(),
                   s0_ptrs.data_ptr() if s0_ptrs is not None else None,
                   s1_ptrs.data_ptr() if s1_ptrs is not None else None, ema_ptrs.data_ptr(), *self._tab(),
                   float(w0), float(w1), float(w2), self._stream())
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    """torch.optim.AdamW (train/train_transformer.py:2125-2147) as ONE multi-tensor launch per step.
+
+    Same constructor, same update rule and the same per-parameter state (`step`, `exp_avg`, `exp_avg_sq`), so
+    `state_dict()` / `load_state_dict()` interchange with torch.optim.AdamW checkpoints
+    (train/train_transformer.py:752-820).  What is fused into the pass: the GradScaler's unscale and inf check
+    (`scaler.step(opt)` hands `grad_scale` / `found_inf` over as device tensors, :1203-1232 -- a skipped step costs no
+    host synchronisation: the step counter lives on the device too) and, with `step(zero_grad=True)`, the gradient
+    clear the next accumulation pass needs.  28 B (+4) per parameter, once.  `amsgrad` / `maximize` are not built."""
+
+    _step_supports_amp_scaling = True
+    fused_zero_grad = True
+
+    def __init__(self, params, lr: float = 1e-3, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 1e-2, amsgrad: bool = False, *, maximize: bool = False, foreach=None,
+                 capturable: bool = False, differentiable: bool = False, fused=None):
+        if amsgrad or maximize or differentiable:
+            raise NotImplementedError("vsn_b200 FusedAdamW: amsgrad / maximize / differentiable are not built")
+        if lr < 0.0 or eps < 0.0 or not 0.0 <= betas[0] < 1.0 or not 0.0 <= betas[1] < 1.0 or weight_decay < 0.0:
+            raise ValueError("invalid AdamW hyper-parameter")
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=False, maximize=False,
+                        foreach=None, capturable=False, differentiable=False, fused=None)
+        super().__init__(params, defaults)
+        self._plans: Dict[tuple, dict] = {}
+        self._step_dev: Optional[torch.Tensor] = None      # one counter for all parameters (they always step together)
+        self._ctl: Optional[torch.Tensor] = None
+
+    # -- state ------------------------------------------------------------------------------------
+    def _init_state(self, p: torch.nn.Parameter) -> None:
+        st = self.state[p]
+        if "exp_avg" not in st:
+            st["step"] = torch.zeros((), dtype=F32)
+            st["exp_avg"] = torch.zeros_like(p.detach(), memory_format=torch.contiguous_format)
+            st["exp_avg_sq"] = torch.zeros_like(p.detach(), memory_format=torch.contiguous_format)
+
+    def _device_step(self, dev) -> torch.Tensor:
+        if self._step_dev is None:
+            steps = {float(st["step"]) for st in self.state.values() if "step" in st}
+            if len(steps) > 1:
+                raise NotImplementedError("vsn_b200 FusedAdamW keeps one step count: the loaded state has several")
+            self._step_dev = torch.full((1,), steps.pop() if steps else 0.0, device=dev, dtype=F32)
+            self._ctl = torch.zeros(4, device=dev, dtype=F32)
+        return self._step_dev
+
+    def state_dict(self) -> Dict[str, Any]:
+        if self._step_dev is not None:                      # checkpoint time: one host read of the counter
+            n = float(self._step_dev.item())
+            for st in self.state.values():
+                if "step" in st:
+                    st["step"] = torch.tensor(n, dtype=F32)
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict: Dict[str, Any]) -> None:
+        super().load_state_dict(state_dict)
+        self._plans, self._step_dev, self._ctl = {}, None, None
+
+    # -- one launch per set of groups that share (lr, betas, eps) ------------------------------------
+    def _plan(self, ps: List[torch.nn.Parameter], wds: List[float]) -> dict:
+        key = tuple((p.data_ptr(), p.numel(), self.state[p]["exp_avg"].data_ptr(), self.state[p]["exp_avg_sq"].data_ptr())
+                    for p in ps)
+        pl = self._plans.get(key)
+        if pl is None:
+            for p in ps:
+                if p.dtype != F32 or not p.is_cuda or not p.is_contiguous():
+                    raise RuntimeError("vsn_b200 FusedAdamW needs contiguous fp32 CUDA parameters (there is no CPU fallback)")
+            dev = ps[0].device
+            tab = MultiTensorTable([p.detach() for p in ps], dev)
+            ms = [self.state[p]["exp_avg"] for p in ps]
+            vs = [self.state[p]["exp_avg_sq"] for p in ps]
+            pl = dict(tab=tab, p=tab.ptr_array([p.detach() for p in ps]), m=tab.ptr_array(ms), v=tab.ptr_array(vs),
+                      keep=(ms, vs), gkey=None, g=None, wd=torch.tensor(wds, device=dev, dtype=F32), wds=list(wds))
+            if len(self._plans) > 8:
+                self._plans.clear()
+            self._plans[key] = pl
+        if pl["wds"] != list(wds):
+            pl["wd"].copy_(torch.tensor(wds, dtype=F32), non_blocking=True)
+            pl["wds"] = list(wds)
+        gkey = tuple(p.grad.data_ptr() for p in ps)
+        if gkey != pl["gkey"]:
+            for p in ps:
+                if p.grad.dtype != F32 or not p.grad.is_contiguous():
+                    raise RuntimeError("vsn_b200 FusedAdamW needs contiguous fp32 gradients")
+            pl["g"] = pl["tab"].ptr_array([p.grad for p in ps])
+            pl["gkey"] = gkey
+        return pl
+
+    @torch.no_grad()
+    def step(self, closure: Optional[Callable[[], Any]] = None, *, zero_grad: bool = False):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        sets: Dict[tuple, Tuple[list, list]] = {}
+        for group in self.param_groups:
+            hp = (float(group["lr"]), float(group["betas"][0]), float(group["betas"][1]), float(group["eps"]))
+            ps, wds = sets.setdefault(hp, ([], []))
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                if p.grad.is_sparse:
+                    raise RuntimeError("AdamW does not support sparse gradients")
+                self._init_state(p)
+                ps.append(p)
+                wds.append(float(group["weight_decay"]))
+        sets = {hp: v for hp, v in sets.items() if v[0]}
+        if not sets:
+            return loss
+        betas = {(hp[1], hp[2]) for hp in sets}
+        if len(betas) > 1:
+            raise NotImplementedError("vsn_b200 FusedAdamW keeps one step count / bias correction: one betas pair")
+        dev = next(iter(sets.values()))[0][0].device
+        step = self._device_step(dev)
+        found_inf = getattr(self, "found_inf", None)        # set by GradScaler.step (torch/amp/grad_scaler.py)
+        grad_scale = getattr(self, "grad_scale", None)
+        inv = None
+        if grad_scale is not None:
+            inv = grad_scale.to(device=dev, dtype=F32).reciprocal().reshape(1)
+        if found_inf is not None:
+            found_inf = found_inf.to(device=dev, dtype=F32).reshape(1)
+        b1, b2 = next(iter(betas))
+        _lib.call("vsn_adamw_prepare", step.data_ptr(), found_inf.data_ptr() if found_inf is not None else None,
+                  inv.data_ptr() if inv is not None else None, b1, b2, self._ctl.data_ptr(),
+                  torch.cuda.current_stream().cuda_stream)
+        for (lr, _, _, eps), (ps, wds) in sets.items():
+            pl = self._plan(ps, wds)
+            pl["tab"].adamw(pl["p"], pl["g"], pl["m"], pl["v"], pl["wd"], self._ctl, lr, b1, b2, eps, zero_grad)
+        return loss
 
 
 class SAM(torch.optim.Optimizer):
@@ -211,6 +346,9 @@ class SAM(torch.optim.Optimizer):
             pl = self._get_plan(ps)
             pl["tab"].copy(pl["p"], pl["old"])     # back to "w" from "w + e(w)"
         if scaler is None:
+            if zero_grad and getattr(self.base_optimizer, "fused_zero_grad", False):
+                self.base_optimizer.step(zero_grad=True)      # gradients cleared inside the AdamW pass
+                return
             self.base_optimizer.step()
             if zero_grad:
                 self.zero_grad()

@@ -19,7 +19,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from .ddp import GradAllReduce
-from .optim import SAM, EMAModel
+from .optim import SAM, EMAModel, FusedAdamW
 from .swin import GradSink
 
 
@@ -45,6 +45,7 @@ def param_groups(model: torch.nn.Module):
 class TrainStep:
     """`step(batches)` = one optimiser step over the given micro-batches `[(x [B,1,D,H,W], y [B,K] soft labels)]`.
 
+    fused_adamw optim.FusedAdamW instead of torch.optim.AdamW(fused=True) (identical update)
     ddp_model   a torch DistributedDataParallel wrap of `model`: gradients then travel through autograd and the
                 reducer's hooks exactly as in the reference trainer (no in-place accumulation, no graph)
     grad_sync   a `ddp.GradAllReduce` over `model.parameters()` built by the caller (N > 1); without one the step
@@ -59,7 +60,7 @@ class TrainStep:
     def __init__(self, model: torch.nn.Module, *, lr: float = 1e-4, weight_decay: float = 0.05, use_sam: bool = False,
                  sam_rho: float = 0.05, use_ema: bool = True, ema_decay: float = 0.999, smoothing: float = 0.1,
                  ddp_model: Optional[torch.nn.Module] = None, grad_sync: Optional[GradAllReduce] = None,
-                 graph: bool = False, graph_comm: bool = True):
+                 graph: bool = False, graph_comm: bool = True, fused_adamw: bool = True):
         self.module = model                       # the bare module (EMA / parameters)
         self.model = ddp_model if ddp_model is not None else model   # what forward is called on
         self.autograd_grads = ddp_model is not None
@@ -70,11 +71,14 @@ class TrainStep:
         else:
             self.grad_sync = grad_sync if grad_sync is not None else GradAllReduce(model.parameters())
         groups = param_groups(model)
+        # fused_adamw: optim.FusedAdamW (one multi-tensor launch: update + gradient clear); off: torch's fused AdamW, the
+        # reference's choice (train/train_transformer.py:2125-2131) -- same update rule, same state layout
+        base = FusedAdamW if fused_adamw else torch.optim.AdamW
         if use_sam:
-            self.opt = SAM(groups, torch.optim.AdamW, rho=sam_rho, adaptive=False, lr=lr, weight_decay=weight_decay,
-                           fused=True)
+            self.opt = SAM(groups, base, rho=sam_rho, adaptive=False, lr=lr, weight_decay=weight_decay, fused=True)
         else:
-            self.opt = torch.optim.AdamW(groups, lr=lr, weight_decay=weight_decay, fused=True)
+            self.opt = base(groups, lr=lr, weight_decay=weight_decay, fused=True)
+        self.fused_adamw = fused_adamw
         self.use_sam = use_sam
         self.ema = EMAModel(model=model, decay=ema_decay) if use_ema else None
         self.smoothing = smoothing
@@ -208,8 +212,13 @@ class TrainStep:
             self.opt.first_step(zero_grad=False)
             self._zero_grad()
             self._accumulate(batches)
-            self.opt.second_step(zero_grad=False)
-            self._zero_grad()
+            if self.fused_adamw:
+                self.opt.second_step(zero_grad=True)       # restore + AdamW; the AdamW pass clears the gradients
+            else:
+                self.opt.second_step(zero_grad=False)
+                self._zero_grad()
+        elif self.fused_adamw:
+            self.opt.step(zero_grad=True)
         else:
             self.opt.step()
             self._zero_grad()
