@@ -325,7 +325,7 @@ def config_dict(args, world):
     name = f"Swin-3D (Swin-T, swin-{args.classes}c geometry)" if args.model == "swin" else f"ViT-3D (ViT-S, vit-{args.classes}c geometry)"
     in_mb = args.batch * args.micro_batches * vol[0] * vol[1] * vol[2] * 2 / 1e6
     return {"workload": f"{name} {'SAM(AdamW)' if args.sam else 'AdamW'}{'' if args.no_ema else '+EMA'}"
-                        f"{'+MixUp' if args.mixup else ''} training step",
+                        f"{'+MixUp+z-score on device' if args.mixup else ''} training step",
             "volume": list(vol), "micro_batch": args.batch, "micro_batches_per_step": args.micro_batches,
             "global_batch": args.batch * args.micro_batches * world, "parallelism": f"dp{world}",
             "l2": f"per-step inputs ({in_mb:.0f} MB) and activations (GBs) exceed the 126 MB L2; no explicit flush"}
@@ -549,7 +549,8 @@ class Workload:
             self.mix = {"lam": lam.to(be.dev), "perm": perm.to(be.dev), "i": 0, "n": n}
 
     def _prepare(self, batches):
-        """BASELINE config 3: MixUp on the device (dataset/dataset.py:230-286) -- input preparation, one kernel per
+        """BASELINE config 3: MixUp (dataset/dataset.py:230-286) and the z-score that follows it in the reference's
+        transform chain (train/train_transformer.py:1729-1752) on the device -- input preparation, three kernels per
         micro-batch for the volumes; the [B, K] labels are mixed by torch."""
         if self.mix is None:
             return batches
@@ -560,7 +561,8 @@ class Workload:
         out = []
         for j, (x, y) in enumerate(batches):
             lam, perm = mx["lam"][i, j], mx["perm"][i, j]
-            out.append((ops.mixup(x, lam, perm), lam[:, None] * y + (1 - lam[:, None]) * y[perm.long()]))
+            # MixUp + NormalizeIntensity() of the raw fp16 volumes in two passes (statistics, mix + z-score + write)
+            out.append((ops.mixup_zscore(x, lam, perm)[0], lam[:, None] * y + (1 - lam[:, None]) * y[perm.long()]))
         return out
 
     def step_resident(self):

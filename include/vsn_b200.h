@@ -97,9 +97,20 @@ int vsn_grid_copy(const float* src, int sD, int sH, int sW, float* dst, int dD, 
 int vsn_merge_gather(float* x, int pD, int pH, int pW, int rD, int rH, int rW, float* out, int B, int C, int scatter,
                      void* stream);
 /* MixUp of fp16 volumes on the device (dataset/dataset.py:230-286, `sample1*alpha + sample2*(1-alpha)`):
- * out[b] = lam[b]*x[b] + (1-lam[b])*x[perm[b]]; lam [B] fp32 (1 = sample left alone), perm [B] int32; not in place. */
+ * out[b] = fp16(fp16(lam[b]*x[b]) + (1-lam[b])*x[perm[b]]) -- the reference's in-place fp16 mul_ then add_;
+ * lam [B] fp32 (1 = sample left alone), perm [B] int32; not in place. */
 int vsn_mixup_f16(const void* x, void* out, const float* lam, const int* perm, int B, long long elems_per_sample,
                   void* stream);
+/* The input step before the path, on the device: monai NormalizeIntensity() of the (optionally
+ * mixed) fp16 volume -- (x - mean) / std over the whole image, population std, no division when std == 0 -- which
+ * train/train_transformer.py:1729-1752 puts last in every transform chain, after dataset/dataset.py:230-286's MixUp.
+ * vsn_volume_stats_f16: stats[b] = {mean, 1/std} of mix(x[b], x[perm[b]]) (lam/perm nullable: no MixUp);
+ * scratch = 2*B doubles, zero on entry, zero again on exit.  vsn_mixup_zscore_f16: out[b] = fp16((mix - mean) * rstd);
+ * in place only without MixUp. */
+int vsn_volume_stats_f16(const void* x, const float* lam, const int* perm, int B, long long elems_per_sample,
+                         double* scratch, float* stats, void* stream);
+int vsn_mixup_zscore_f16(const void* x, void* out, const float* lam, const int* perm, const float* stats, int B,
+                         long long elems_per_sample, void* stream);
 int vsn_cast_rows_bf16(const float* src, void* dst, const float* row_scale, int rows_per_group, long long rows, int C,
                        void* stream);
 int vsn_cast_bf16(const float* src, void* dst, long long n, void* stream);

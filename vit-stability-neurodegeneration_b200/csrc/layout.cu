@@ -270,8 +270,14 @@ __global__ void vit_assemble_bwd_kernel(const float* __restrict__ dx, float* __r
   }
 }
 
-// MixUp of fp16 volumes (dataset/dataset.py:276-281: sample1 * alpha + sample2 * (1 - alpha)):
-// out[b] = lam[b] * x[b] + (1 - lam[b]) * x[perm[b]], fp32 arithmetic, 16-byte accesses.  lam[b] == 1 copies x[b].
+// MixUp of fp16 volumes (dataset/dataset.py:276-281): the reference works in place on the fp16 tensors,
+// `sample1.mul_(alpha)` (rounds to fp16) then `.add_(sample2, alpha=1 - alpha)` (fp32 arithmetic, one more rounding):
+// out[b] = fp16(fp16(lam[b] * x[b]) + fp16(1 - lam[b]) * x[perm[b]]), 16-byte accesses.  lam[b] == 1 copies x[b].
+// (The reference mixes on the CPU: `mul_` takes its Python scalar as fp32, `add_` rounds its alpha to the TENSOR's dtype
+// first -- checked against torch's CPU kernels element by element -- and both compute in fp32.)
+__device__ __forceinline__ float mix_f16(float l, float a, float c) {
+  return fmaf(__half2float(__float2half_rn(1.0f - l)), c, __half2float(__float2half_rn(l * a)));
+}
 __global__ void mixup_f16_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, const float* __restrict__ lam,
                                  const int* __restrict__ perm, int B, long long vec_per_sample) {
   const long long total = static_cast<long long>(B) * vec_per_sample;
@@ -290,7 +296,7 @@ __global__ void mixup_f16_kernel(const uint4* __restrict__ x, uint4* __restrict_
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float2 fa = __half22float2(ah[k]), fc = __half22float2(ch[k]);
-        oh[k] = __floats2half2_rn(fmaf(l, fa.x, (1.0f - l) * fc.x), fmaf(l, fa.y, (1.0f - l) * fc.y));
+        oh[k] = __floats2half2_rn(mix_f16(l, fa.x, fc.x), mix_f16(l, fa.y, fc.y));
       }
       a = o;
     }
@@ -304,6 +310,108 @@ inline unsigned grid_for(long long total, int block) {
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   return static_cast<unsigned>(g);
+}
+
+
+// ---- the input step before the path: fp16 cache -> MixUp -> z-score, all on the device ----
+// Per-volume sum and sum of squares of the (optionally mixed) fp16 volume, fp32 per thread, double across threads:
+// monai NormalizeIntensity() = (x - mean) / std over the whole image, population std, std == 0 -> no division
+// (train/train_transformer.py:1729-1752 puts it last in every transform chain, i.e. after dataset/dataset.py's MixUp).
+// grid = (chunks, B); scratch[b] = {sum, sumsq} must be zero.
+__global__ void __launch_bounds__(256) volume_stats_f16_kernel(const uint4* __restrict__ x, const float* __restrict__ lam,
+                                                               const int* __restrict__ perm, long long vec_per_sample,
+                                                               double* __restrict__ scratch) {
+  const int b = blockIdx.y;
+  const float l = lam != nullptr ? lam[b] : 1.0f;
+  const uint4* xa = x + static_cast<long long>(b) * vec_per_sample;
+  const uint4* xc = l != 1.0f ? x + static_cast<long long>(perm[b]) * vec_per_sample : nullptr;
+  double s1 = 0.0, s2 = 0.0;
+  for (long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < vec_per_sample;
+       i0 += static_cast<long long>(gridDim.x) * blockDim.x * 8) {
+    float f1 = 0.f, f2 = 0.f;                   // at most 64 voxels in fp32 before they go to the double sums
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const long long i = i0 + static_cast<long long>(u) * gridDim.x * blockDim.x;
+      if (i < vec_per_sample) {
+        const uint4 a = xa[i];
+        const __half2* ah = reinterpret_cast<const __half2*>(&a);
+        uint4 c = make_uint4(0, 0, 0, 0);
+        if (xc != nullptr) c = xc[i];
+        const __half2* ch = reinterpret_cast<const __half2*>(&c);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float2 v = __half22float2(ah[k]);
+          if (xc != nullptr) {
+            const float2 w = __half22float2(ch[k]);
+            v = __half22float2(__floats2half2_rn(mix_f16(l, v.x, w.x), mix_f16(l, v.y, w.y)));
+          }
+          f1 += v.x + v.y;
+          f2 = fmaf(v.x, v.x, fmaf(v.y, v.y, f2));
+        }
+      }
+    }
+    s1 += f1; s2 += f2;
+  }
+  __shared__ double r1[8], r2[8];
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = s1; r2[threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, c = 0.0;
+    for (int i = 0; i < 8; ++i) { a += r1[i]; c += r2[i]; }
+    atomicAdd(scratch + 2 * b, a);
+    atomicAdd(scratch + 2 * b + 1, c);
+  }
+}
+
+// stats[b] = {mean, 1/std} (1 when std == 0); clears the scratch sums for the next batch
+__global__ void volume_stats_finish_kernel(double* __restrict__ scratch, float* __restrict__ stats, int B, double n) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double mean = scratch[2 * b] / n;
+  double var = scratch[2 * b + 1] / n - mean * mean;
+  var = var > 0.0 ? var : 0.0;
+  const double sd = sqrt(var);
+  stats[2 * b] = static_cast<float>(mean);
+  stats[2 * b + 1] = sd > 0.0 ? static_cast<float>(1.0 / sd) : 1.0f;
+  scratch[2 * b] = 0.0;
+  scratch[2 * b + 1] = 0.0;
+}
+
+// out[b] = fp16((mix(x[b], x[perm[b]]) - mean[b]) * rstd[b]): MixUp and NormalizeIntensity in one pass over the volume
+__global__ void __launch_bounds__(256) mixup_zscore_f16_kernel(const uint4* __restrict__ x, uint4* __restrict__ out,
+                                                               const float* __restrict__ lam, const int* __restrict__ perm,
+                                                               const float* __restrict__ stats, int B,
+                                                               long long vec_per_sample) {
+  pdl_trigger();
+  const long long total = static_cast<long long>(B) * vec_per_sample;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / vec_per_sample);
+    const long long r = i - static_cast<long long>(b) * vec_per_sample;
+    const float l = lam != nullptr ? lam[b] : 1.0f;
+    const float mean = stats[2 * b], rstd = stats[2 * b + 1];
+    const uint4 a = x[i];
+    uint4 c = make_uint4(0, 0, 0, 0);
+    if (l != 1.0f) c = x[static_cast<long long>(perm[b]) * vec_per_sample + r];
+    const __half2* ah = reinterpret_cast<const __half2*>(&a);
+    const __half2* ch = reinterpret_cast<const __half2*>(&c);
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 v = __half22float2(ah[k]);
+      if (l != 1.0f) {
+        const float2 w = __half22float2(ch[k]);
+        v = __half22float2(__floats2half2_rn(mix_f16(l, v.x, w.x), mix_f16(l, v.y, w.y)));
+      }
+      oh[k] = __floats2half2_rn((v.x - mean) * rstd, (v.y - mean) * rstd);
+    }
+    out[i] = o;
+  }
 }
 
 }  // namespace
@@ -448,6 +556,40 @@ extern "C" int vsn_mixup_f16(const void* x, void* out, const float* lam, const i
   if (total == 0) return 0;
   mixup_f16_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), lam, perm, B, elems_per_sample / 8);
+  VSN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vsn_volume_stats_f16(const void* x, const float* lam, const int* perm, int B, long long elems_per_sample,
+                                    double* scratch, float* stats, void* stream) {
+  VSN_CHECK(elems_per_sample % 8 == 0, "vsn_volume_stats_f16: elements per sample must be a multiple of 8");
+  VSN_CHECK(reinterpret_cast<uintptr_t>(x) % 16 == 0, "vsn_volume_stats_f16: 16-byte aligned volumes expected");
+  VSN_CHECK((lam == nullptr) == (perm == nullptr), "vsn_volume_stats_f16: lam and perm go together");
+  if (B == 0) return 0;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long vec = elems_per_sample / 8;
+  int chunks = ceil_div(2 * vsn_num_sms(), B);
+  const long long maxc = (vec + 255) / 256;
+  if (chunks > maxc) chunks = static_cast<int>(maxc);
+  if (chunks < 1) chunks = 1;
+  volume_stats_f16_kernel<<<dim3(chunks, B), 256, 0, s>>>(reinterpret_cast<const uint4*>(x), lam, perm, vec, scratch);
+  VSN_LAUNCH_CHECK();
+  volume_stats_finish_kernel<<<ceil_div(B, 128), 128, 0, s>>>(scratch, stats, B, static_cast<double>(elems_per_sample));
+  VSN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vsn_mixup_zscore_f16(const void* x, void* out, const float* lam, const int* perm, const float* stats, int B,
+                                    long long elems_per_sample, void* stream) {
+  VSN_CHECK(elems_per_sample % 8 == 0, "vsn_mixup_zscore_f16: elements per sample must be a multiple of 8");
+  VSN_CHECK(reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0,
+            "vsn_mixup_zscore_f16: 16-byte aligned volumes expected");
+  VSN_CHECK(x != out || lam == nullptr, "vsn_mixup_zscore_f16: MixUp is not in place (a sample is read as its partner's input)");
+  VSN_CHECK((lam == nullptr) == (perm == nullptr), "vsn_mixup_zscore_f16: lam and perm go together");
+  const long long total = static_cast<long long>(B) * (elems_per_sample / 8);
+  if (total == 0) return 0;
+  mixup_zscore_f16_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), lam, perm, stats, B, elems_per_sample / 8);
   VSN_LAUNCH_CHECK();
   return 0;
 }

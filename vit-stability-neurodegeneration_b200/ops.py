@@ -5,7 +5,7 @@ computes with torch ops; torch is the allocator and the stream owner.
 """
 from __future__ import annotations
 
-from typing import Optional, Sequence
+from typing import Optional, Sequence, Tuple
 
 import torch
 
@@ -263,6 +263,45 @@ def mixup(x: torch.Tensor, lam: torch.Tensor, perm: torch.Tensor) -> torch.Tenso
         _lib.WORK = (0, x.numel() * 6)
     _lib.call("vsn_mixup_f16", _p(x), _p(out), _p(lam), _p(perm), B, per, _stream())
     return out
+
+
+_STATS_SCRATCH = {}
+
+
+def volume_stats(x: torch.Tensor, lam: Optional[torch.Tensor] = None, perm: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[B, 2] = (mean, 1/std) of every (optionally mixed) fp16 volume: the statistics of monai's NormalizeIntensity()
+    (train/train_transformer.py:1729-1752), population std, 1/std := 1 when std == 0."""
+    assert x.dtype == torch.float16 and x.is_contiguous()
+    _require_cuda(x)
+    B = x.shape[0]
+    per = x.numel() // B
+    key = (x.device, B)
+    if key not in _STATS_SCRATCH:
+        _STATS_SCRATCH[key] = torch.zeros(2 * B, device=x.device, dtype=torch.float64)
+    stats = torch.empty((B, 2), device=x.device, dtype=F32)
+    if _lib.PROFILE is not None:
+        _lib.TAG = f"B{B} elems{per} mix={int(lam is not None)}"
+        _lib.WORK = (0, x.numel() * 2 * (2 if lam is not None else 1))
+    _lib.call("vsn_volume_stats_f16", _p(x), _p(lam), _p(perm), B, per, _p(_STATS_SCRATCH[key]), _p(stats), _stream())
+    return stats
+
+
+def mixup_zscore(x: torch.Tensor, lam: Optional[torch.Tensor] = None, perm: Optional[torch.Tensor] = None,
+                 out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """MixUp (dataset/dataset.py:230-286) followed by NormalizeIntensity() of fp16 volumes [B,1,D,H,W] on the device,
+    two passes over the batch (statistics, then mix + normalise + write); returns (normalised fp16 volumes, stats)."""
+    if lam is not None:
+        assert lam.dtype == F32 and perm is not None and perm.dtype == torch.int32
+    stats = volume_stats(x, lam, perm)
+    B = x.shape[0]
+    per = x.numel() // B
+    if out is None:
+        out = torch.empty_like(x)
+    if _lib.PROFILE is not None:
+        _lib.TAG = f"B{B} elems{per} mix={int(lam is not None)}"
+        _lib.WORK = (0, x.numel() * 2 * (3 if lam is not None else 2))
+    _lib.call("vsn_mixup_zscore_f16", _p(x), _p(out), _p(lam), _p(perm), _p(stats), B, per, _stream())
+    return out, stats
 
 
 def cast_rows_bf16(src: torch.Tensor, row_scale=None, rows_per_group=1) -> torch.Tensor:
