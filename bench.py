@@ -291,6 +291,47 @@ def swin_state_shapes(classes):
     return {k: tuple(v.shape) for k, v in m.state_dict().items() if v.is_floating_point()}
 
 
+
+def tta_ensemble_arm(args, dev, subjects=2, snapshots=10, steps=3, warmup=1):
+    """BASELINE config 5: Swin-3D (swin-5c) evaluation with test-time augmentation (8 views: identity, flip, 5 affine,
+    centre crop + resize) and a 10-snapshot ensemble (eval/test_time_augmentation.py:221-354,
+    scripts/transformer.sh:241-266).  A step = `subjects` normalised fp16 volumes copied from pinned host memory, all
+    views written by one kernel, one [subjects*8] forward per snapshot (weights swapped in with load_state_dict), the
+    entropy-weighted averages and the D2H read of the probabilities.  volumes/s = subjects / step time."""
+    import torch
+    import vsn_b200  # noqa: F401
+    from vsn_b200.swin_model import SwinTransformerT
+    from vsn_b200.tta import TestTimeAugmentation, SnapshotEnsemble
+    torch.manual_seed(0)
+    model = SwinTransformerT(in_channels=1, mlp_ratio=4.0, qkv_bias=True, dropout=0.0, attention_dropout=0.0,
+                             stochastic_depth_prob=0.15, num_classes=5, norm_layer=torch.nn.LayerNorm, **SWIN).to(dev).eval()
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    snaps = [sd0] + [{k: (v + 1e-3 * torch.randn_like(v) if v.is_floating_point() else v.clone()) for k, v in sd0.items()}
+                     for _ in range(snapshots - 1)]
+    tta = TestTimeAugmentation(model, dev, num_samples=5, seed=0)
+    ens = SnapshotEnsemble(model, snaps, tta)
+    vol = VOLUMES["swin"]
+    host = torch.randn(subjects, 1, *vol).half().pin_memory()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    probs = None
+    for i in range(warmup + steps):
+        if i == warmup:
+            torch.cuda.synchronize()
+            e0.record()
+        probs = ens.predict(host).cpu()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    views = tta.get_num_augmentations()
+    return {"value": round(subjects / (ms * 1e-3), 2), "unit": "volumes/s", "ms_per_step": round(ms, 3),
+            "config": {"workload": "Swin-3D (Swin-T, swin-5c) inference, test-time augmentation + snapshot ensemble",
+                       "volume": list(vol), "subjects_per_step": subjects, "views": views, "snapshots": snapshots,
+                       "forward_volumes_per_step": subjects * views * snapshots},
+            "forward_volumes_per_s": round(subjects * views * snapshots / (ms * 1e-3), 1),
+            "h2d_bytes_per_step": int(host.numel() * 2), "d2h_bytes_per_step": int(probs.numel() * 4),
+            "probabilities_sum_to_one": bool(float((probs.sum(-1) - 1).abs().max()) < 1e-4)}
+
+
 def eager_cuda_arm(args, steps=3, warmup=2):
     """The unmodified reference, eager PyTorch on this GPU: fp16 autocast + GradScaler + TF32 (the trainer's own
     precision setup, train/train_transformer.py:91-92,1068-1072,1141), same batch schedule as the native arm."""
@@ -802,6 +843,12 @@ def native_main(args):
     # ---- baselines on rank 0 at N = 1 only -------------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.stub:
+        if not args.no_extras and args.model == "swin":
+            try:
+                extras["swin5c_tta_ensemble_infer"] = tta_ensemble_arm(args, be.dev)
+            except RuntimeError as e:
+                extras["swin5c_tta_ensemble_infer"] = {"unavailable": str(e).splitlines()[0][:200]}
+            be.torch.cuda.empty_cache()
         if not args.no_extras:
             try:
                 extras["eager_cuda_baseline"] = eager_cuda_arm(args)

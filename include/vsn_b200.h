@@ -111,6 +111,12 @@ int vsn_volume_stats_f16(const void* x, const float* lam, const int* perm, int B
                          double* scratch, float* stats, void* stream);
 int vsn_mixup_zscore_f16(const void* x, void* out, const float* lam, const int* perm, const float* stats, int B,
                          long long elems_per_sample, void* stream);
+/* All test-time-augmentation views of B fp16 volumes in one launch (eval/test_time_augmentation.py:221-354: identity,
+ * flip, RandAffine rotations + translations with bilinear sampling and border padding, centre crop + trilinear resize):
+ * out[b][v] = trilinear sample of vol[b] at views[v] = {3x4 row-major matrix: output voxel index (d,h,w,1) -> source
+ * voxel coordinates; lo[3], hi[3]: the box coordinates and upper neighbours are clamped to (the volume, or the crop)}.
+ * Integer-valued maps (identity, flip) copy bit-exactly. */
+int vsn_tta_views_f16(const void* vol, void* out, const float* views, int B, int V, int D, int H, int W, void* stream);
 int vsn_cast_rows_bf16(const float* src, void* dst, const float* row_scale, int rows_per_group, long long rows, int C,
                        void* stream);
 int vsn_cast_bf16(const float* src, void* dst, long long n, void* stream);

@@ -28,6 +28,7 @@ SIGNATURES = {
     "vsn_mixup_f16": [_p, _p, _p, _p, _i, _ll, _p],
     "vsn_volume_stats_f16": [_p, _p, _p, _i, _ll, _p, _p, _p],
     "vsn_mixup_zscore_f16": [_p, _p, _p, _p, _p, _i, _ll, _p],
+    "vsn_tta_views_f16": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
     "vsn_cast_rows_bf16": [_p, _p, _p, _i, _ll, _i, _p],
     "vsn_cast_bf16": [_p, _p, _ll, _p],
     "vsn_token_mean": [_p, _p, _i, _i, _i, _i, _p],

@@ -414,6 +414,55 @@ __global__ void __launch_bounds__(256) mixup_zscore_f16_kernel(const uint4* __re
   }
 }
 
+
+// ---- test-time augmentation views (eval/test_time_augmentation.py:221-354) -------------------------------------
+// out[b, v, z] = trilinear sample of vol[b] at M_v * (z, 1): every view of the reference's TTA -- identity, flip,
+// small rotations + translations (RandAffine, bilinear, border padding), centre crop + trilinear resize -- is an affine
+// map from the output voxel index to source voxel coordinates, so all views of all volumes come out of one launch and
+// the model runs once on a [B*V] batch instead of V batch-1 forwards with host-side resampling in between.
+// views [V][18]: a row-major 3x4 matrix (d, h, w), then the box lo[3], hi[3] (voxel indices) the coordinates and the
+// upper neighbours are clamped to: the whole volume for padding_mode = "border", the crop box for crop + resize.
+__global__ void __launch_bounds__(256) tta_views_f16_kernel(const __half* __restrict__ vol, __half* __restrict__ out,
+                                                            const float* __restrict__ mats, int B, int V, int D, int H,
+                                                            int W) {
+  const long long per = static_cast<long long>(D) * H * W;
+  const long long total = static_cast<long long>(B) * V * per;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long t = idx;
+    const int w = static_cast<int>(t % W); t /= W;
+    const int h = static_cast<int>(t % H); t /= H;
+    const int d = static_cast<int>(t % D); t /= D;
+    const int v = static_cast<int>(t % V);
+    const int b = static_cast<int>(t / V);
+    const float* m = mats + v * 18;
+    float sd = fmaf(m[0], d, fmaf(m[1], h, fmaf(m[2], w, m[3])));
+    float sh = fmaf(m[4], d, fmaf(m[5], h, fmaf(m[6], w, m[7])));
+    float sw = fmaf(m[8], d, fmaf(m[9], h, fmaf(m[10], w, m[11])));
+    sd = fminf(fmaxf(sd, m[12]), m[15]);
+    sh = fminf(fmaxf(sh, m[13]), m[16]);
+    sw = fminf(fmaxf(sw, m[14]), m[17]);
+    const int d0 = static_cast<int>(sd), h0 = static_cast<int>(sh), w0 = static_cast<int>(sw);
+    const int d1 = min(d0 + 1, static_cast<int>(m[15])), h1 = min(h0 + 1, static_cast<int>(m[16])),
+              w1 = min(w0 + 1, static_cast<int>(m[17]));
+    const float fd = sd - d0, fh = sh - h0, fw = sw - w0;
+    const __half* src = vol + static_cast<long long>(b) * per;
+    auto at = [&](int a, int c, int e) { return __half2float(src[(static_cast<long long>(a) * H + c) * W + e]); };
+    float r;
+    if (fd == 0.f && fh == 0.f && fw == 0.f) {
+      r = at(d0, h0, w0);                                    // identity / flip: a bit-exact copy
+    } else {
+      const float c00 = at(d0, h0, w0) * (1.f - fw) + at(d0, h0, w1) * fw;
+      const float c01 = at(d0, h1, w0) * (1.f - fw) + at(d0, h1, w1) * fw;
+      const float c10 = at(d1, h0, w0) * (1.f - fw) + at(d1, h0, w1) * fw;
+      const float c11 = at(d1, h1, w0) * (1.f - fw) + at(d1, h1, w1) * fw;
+      const float c0 = c00 * (1.f - fh) + c01 * fh, c1 = c10 * (1.f - fh) + c11 * fh;
+      r = c0 * (1.f - fd) + c1 * fd;
+    }
+    out[idx] = __float2half_rn(r);
+  }
+}
+
 }  // namespace
 
 // in_dtype: 0 fp32, 1 fp16, 2 bf16.  out_bf16: 1 -> bf16 rows (GEMM operand), 0 -> fp32 rows (feeds LayerNorm).
@@ -590,6 +639,17 @@ extern "C" int vsn_mixup_zscore_f16(const void* x, void* out, const float* lam, 
   if (total == 0) return 0;
   mixup_zscore_f16_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), lam, perm, stats, B, elems_per_sample / 8);
+  VSN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vsn_tta_views_f16(const void* vol, void* out, const float* mats, int B, int V, int D, int H, int W,
+                                 void* stream) {
+  const long long total = static_cast<long long>(B) * V * D * H * W;
+  if (total == 0) return 0;
+  VSN_CHECK(vol != out, "vsn_tta_views_f16: not in place");
+  tta_views_f16_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(vol), reinterpret_cast<__half*>(out), mats, B, V, D, H, W);
   VSN_LAUNCH_CHECK();
   return 0;
 }

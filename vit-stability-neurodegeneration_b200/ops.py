@@ -304,6 +304,22 @@ def mixup_zscore(x: torch.Tensor, lam: Optional[torch.Tensor] = None, perm: Opti
     return out, stats
 
 
+def tta_views(x: torch.Tensor, mats: torch.Tensor) -> torch.Tensor:
+    """[B,1,D,H,W] fp16 volumes, [V,18] fp32 views (3x4 matrix + clamp box, see tta.py) -> [B*V,1,D,H,W] fp16
+    (sample-major): every TTA view of every volume in one launch (eval/test_time_augmentation.py:221-354)."""
+    assert x.dtype == torch.float16 and x.is_contiguous() and x.ndim == 5 and x.shape[1] == 1
+    assert mats.dtype == F32 and mats.is_contiguous() and mats.ndim == 2 and mats.shape[1] == 18
+    _require_cuda(x, mats)
+    B, _, D, H, W = x.shape
+    V = mats.shape[0]
+    out = torch.empty((B * V, 1, D, H, W), device=x.device, dtype=torch.float16)
+    if _lib.PROFILE is not None:
+        _lib.TAG = f"B{B} V{V} vol{D}x{H}x{W}"
+        _lib.WORK = (0, 2 * (x.numel() + out.numel()))
+    _lib.call("vsn_tta_views_f16", _p(x), _p(out), _p(mats), B, V, D, H, W, _stream())
+    return out
+
+
 def cast_rows_bf16(src: torch.Tensor, row_scale=None, rows_per_group=1) -> torch.Tensor:
     rows, C = src.shape
     assert src.dtype == F32 and src.is_contiguous()
