@@ -55,6 +55,9 @@ def parse(argv=None):
     ap.add_argument("--mixup", action="store_true", help="MixUp the volumes and labels on the device every step")
     ap.add_argument("--no-ema", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of graph replay")
+    ap.add_argument("--no-fuse-micro", action="store_true",
+                    help="accumulate the micro-batches one forward/backward at a time, as the reference's loop does, "
+                         "instead of one pass over their concatenation (same gradients)")
     ap.add_argument("--no-graph-comm", action="store_true",
                     help="N>1, graph mode: reduce the buckets after the last replay instead of inside the graph")
     ap.add_argument("--torch-ddp", action="store_true", help="N>1: use torch DDP instead of vsn_b200.ddp.GradAllReduce")
@@ -369,6 +372,7 @@ def config_dict(args, world):
                         f"{'+MixUp+z-score on device' if args.mixup else ''} training step",
             "volume": list(vol), "micro_batch": args.batch, "micro_batches_per_step": args.micro_batches,
             "global_batch": args.batch * args.micro_batches * world, "parallelism": f"dp{world}",
+            "micro_batches_fused": bool(not args.no_fuse_micro and not args.torch_ddp and args.micro_batches > 1),
             "l2": f"per-step inputs ({in_mb:.0f} MB) and activations (GBs) exceed the 126 MB L2; no explicit flush"}
 
 
@@ -518,7 +522,7 @@ class CudaBackend:
                 sync = GradAllReduce(model.parameters(), bucket_mb=25.0, buffers=model.buffers())
         graph = not args.no_graph and ddp is None
         ts = TrainStep(model, use_sam=args.sam, use_ema=not args.no_ema, ddp_model=ddp, grad_sync=sync, graph=graph,
-                       graph_comm=not args.no_graph_comm)
+                       graph_comm=not args.no_graph_comm, fuse_micro_batches=not args.no_fuse_micro)
         G = args.micro_batches
         vol = VOLUMES[args.model]
         host = [synth_batch(args.batch, args.classes, seed=1234 + self.rank * 100 + i, volume=vol) for i in range(G)]
@@ -641,7 +645,8 @@ class Workload:
     def launches_per_step(self, eager_delta_per_step):
         ts = self.ts
         passes = 2 if self.args.sam else 1
-        graph = ts.graph_kernel_nodes * self.args.micro_batches * passes if ts.use_graph else 0
+        replays = 1 if ts.fuse_micro_batches else self.args.micro_batches
+        graph = ts.graph_kernel_nodes * replays * passes if ts.use_graph else 0
         return int(eager_delta_per_step + graph)
 
     def replicas_in_sync(self):
@@ -839,6 +844,21 @@ def native_main(args):
         gc.collect()
         be.torch.cuda.empty_cache()
         be.sync_all()
+        if not args.no_fuse_micro and args.micro_batches > 1 and not args.torch_ddp:
+            # the same step with the micro-batches accumulated one forward/backward at a time, as the reference's loop
+            # does (train/train_transformer.py:1111-1190): what `micro_batches_fused` buys, stated beside the headline
+            a3 = argparse.Namespace(**vars(args))
+            a3.no_fuse_micro = True
+            w3 = be.build(a3)
+            m3 = measure(be, w3, a3, max(2, args.steps // 2), 3)
+            extras["micro_batches_one_by_one"] = {
+                "config": config_dict(a3, world), "value": round(m3["value"], 2), "unit": "volumes/s",
+                "ms_per_step": round(m3["ms"] / max(2, args.steps // 2), 3),
+                "e2e": {"value": round(m3["e2e"], 2), "unit": "volumes/s"}}
+            del w3
+            gc.collect()
+            be.torch.cuda.empty_cache()
+            be.sync_all()
 
     # ---- baselines on rank 0 at N = 1 only -------------------------------------------------------------------------
     cpu = None

@@ -269,3 +269,31 @@ def test_train_step_fused_adamw_equals_torch_adamw():
         den = sum(float((y ** 2).sum()) for y in finals[1])
         # (measured 1.9e-3: a weight that differs in its last fp32 bit can round to the other bf16 neighbour for step 2)
         assert den > 0 and (num / den) ** 0.5 < 1e-2, (use_sam, (num / den) ** 0.5)
+
+
+def test_fused_micro_batches_give_the_accumulated_gradient():
+    """train.TrainStep(fuse_micro_batches=True): one pass over the concatenated micro-batches yields the gradient the
+    reference's accumulation loop sums up (train/train_transformer.py:1111-1190: loss_i / n per micro-batch, equal
+    sizes), in eager and in graph mode."""
+    import vsn_b200  # noqa: F401
+    from vsn_b200 import swin_model, train
+    from oracle import cases
+    case = cases.SWIN_CASES["swin_small_even"]
+    g = torch.Generator().manual_seed(6)
+    batches = [(torch.randn(2, *case["input"][1:], generator=g).cuda().half(),
+                torch.softmax(torch.randn(2, case["num_classes"], generator=g), -1).cuda()) for _ in range(3)]
+    grads, losses = {}, {}
+    for mode in ("loop", "fused", "fused_graph"):
+        torch.manual_seed(0)
+        m = swin_model.SwinTransformer(**cases.swin_ctor_kwargs(case)).cuda()
+        ts = train.TrainStep(m, use_ema=False, fuse_micro_batches=mode != "loop", graph=mode == "fused_graph")
+        if mode == "fused_graph":
+            ts._accumulate(batches)              # first call captures (and concatenates); the second one replays with
+            ts._zero_grad()                      # the micro-batches copied into their slices of the static buffers
+        losses[mode] = float(ts._accumulate(batches))
+        grads[mode] = [p.grad.detach().clone() for p in m.parameters()]
+    for mode in ("fused", "fused_graph"):
+        assert abs(losses[mode] - losses["loop"]) < 1e-4 * abs(losses["loop"])
+        num = sum(float(((a - b) ** 2).sum()) for a, b in zip(grads[mode], grads["loop"]))
+        den = sum(float((b ** 2).sum()) for b in grads["loop"])
+        assert (num / den) ** 0.5 < 2e-3, (mode, (num / den) ** 0.5)      # bf16 GEMMs tiled over different row ranges

@@ -45,6 +45,12 @@ def param_groups(model: torch.nn.Module):
 class TrainStep:
     """`step(batches)` = one optimiser step over the given micro-batches `[(x [B,1,D,H,W], y [B,K] soft labels)]`.
 
+    fuse_micro_batches  run the accumulation micro-batches of a pass as ONE forward/backward over their concatenation.
+                The reference accumulates `loss_i / n` over n micro-batches because 8 volumes are what fits its GPUs
+                (train/train_transformer.py:1111-1190); with equal micro-batch sizes and per-sample DropPath / LayerNorm
+                the summed gradient is the gradient of the mean loss over all n*B volumes -- the same numbers, and on
+                180 GB of HBM the 2 x 8 volumes (38 GB of activations) fit at once, so the token dimension of every
+                GEMM doubles and every per-launch cost halves.  The data-parallel exchange is unchanged (one per pass).
     fused_adamw optim.FusedAdamW instead of torch.optim.AdamW(fused=True) (identical update)
     ddp_model   a torch DistributedDataParallel wrap of `model`: gradients then travel through autograd and the
                 reducer's hooks exactly as in the reference trainer (no in-place accumulation, no graph)
@@ -60,7 +66,7 @@ class TrainStep:
     def __init__(self, model: torch.nn.Module, *, lr: float = 1e-4, weight_decay: float = 0.05, use_sam: bool = False,
                  sam_rho: float = 0.05, use_ema: bool = True, ema_decay: float = 0.999, smoothing: float = 0.1,
                  ddp_model: Optional[torch.nn.Module] = None, grad_sync: Optional[GradAllReduce] = None,
-                 graph: bool = False, graph_comm: bool = True, fused_adamw: bool = True):
+                 graph: bool = False, graph_comm: bool = True, fused_adamw: bool = True, fuse_micro_batches: bool = False):
         self.module = model                       # the bare module (EMA / parameters)
         self.model = ddp_model if ddp_model is not None else model   # what forward is called on
         self.autograd_grads = ddp_model is not None
@@ -79,6 +85,7 @@ class TrainStep:
         else:
             self.opt = base(groups, lr=lr, weight_decay=weight_decay, fused=True)
         self.fused_adamw = fused_adamw
+        self.fuse_micro_batches = fuse_micro_batches and ddp_model is None
         self.use_sam = use_sam
         self.ema = EMAModel(model=model, decay=ema_decay) if use_ema else None
         self.smoothing = smoothing
@@ -142,7 +149,26 @@ class TrainStep:
         for sh in self._shadows:
             sh.refresh(force=True)
 
+    def _fused(self, batches):
+        """The micro-batches as one batch (see `fuse_micro_batches`); in graph mode, once the graph exists, they are
+        copied straight into their slices of its static input buffers instead of being concatenated first."""
+        x0, y0 = batches[0]
+        if any(x.shape != x0.shape or x.dtype != x0.dtype or y.shape != y0.shape or y.dtype != y0.dtype
+               for x, y in batches[1:]):
+            return batches                 # ragged last accumulation group: plain accumulation
+        B, n = x0.shape[0], len(batches)
+        key = ((n * B,) + tuple(x0.shape[1:]), x0.dtype, (n * B,) + tuple(y0.shape[1:]), y0.dtype, 1)
+        if self.use_graph and self._graph is not None and self._graph_key == key:
+            sx, sy = self._graph[1], self._graph[2]
+            for i, (x, y) in enumerate(batches):
+                sx[i * B:(i + 1) * B].copy_(x, non_blocking=True)
+                sy[i * B:(i + 1) * B].copy_(y, non_blocking=True)
+            return [(sx, sy)]
+        return [(torch.cat([x for x, _ in batches]), torch.cat([y for _, y in batches]))]
+
     def _accumulate(self, batches: Sequence[Tuple[torch.Tensor, torch.Tensor]]) -> torch.Tensor:
+        if self.fuse_micro_batches and len(batches) > 1:
+            batches = self._fused(batches)
         n = len(batches)
         if self.autograd_grads:
             total = None
