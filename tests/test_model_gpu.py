@@ -201,8 +201,17 @@ def test_train_step_graph_matches_eager_over_optimiser_steps():
         assert abs(a - b) < 2e-3 * abs(a), (le, lg)
     for k in pe:
         # Adam turns round-off-level differences of near-zero gradients (atomic summation order) into +-lr steps
-        assert rel_err(pg[k], pe[k]) < 3e-2, k
-        assert rel_err(eg[k], ee[k]) < 3e-2, k
+        a, b, ea, eb = pg[k], pe[k], eg[k], ee[k]
+        if k.endswith("attn.qkv.bias"):
+            # the key bias has NO gradient in exact arithmetic (a constant added to every key shifts all logits of a
+            # row alike): what the kernels deliver there is summation round-off, its sign depends on the order of the
+            # fp32 atomics, and Adam moves each entry by +-lr per step whichever sign it has.  Bound it, compare q and v.
+            C = a.numel() // 3
+            assert float((a[C:2 * C] - b[C:2 * C]).abs().max()) <= 2 * 3 * 1e-3 * 1.01, k
+            keep = torch.cat([torch.arange(0, C), torch.arange(2 * C, 3 * C)]).to(a.device)
+            a, b, ea, eb = a[keep], b[keep], ea[keep], eb[keep]
+        assert rel_err(a, b) < 3e-2, k
+        assert rel_err(ea, eb) < 3e-2, k
 
 
 def test_droppath_factors_one_draw():
@@ -243,29 +252,43 @@ def test_droppath_factors_one_draw():
 
 def _full_size_grad_check(model, g, x, tgt, masks, swin_model):
     """Train-mode forward + backward at full size against the reference's golden: logits, loss, and for every
-    parameter the gradient norm, 256 sampled values and (small tensors) the whole gradient."""
+    parameter the gradient norm, 256 sampled values and (small tensors) the whole gradient.
+
+    The pass runs TWICE and a parameter's bound is TOL plus twice its own run-to-run difference.  For Swin that
+    difference is ~1e-7 (the window kernels are bit-reproducible, weight gradients see fp32 atomics) and the bound is TOL.  For ViT the dense attention
+    backward sums dQ over its key tiles with fp32 atomics: a different order moves the sum by an ulp, its bf16 rounding
+    flips for 2e-5 of the elements (scripts/exp_determinism.py), and this synthetic-weight ViT-S multiplies such a
+    perturbation by ~3 per layer on the way down (1e-7 at layer 11, 4e-3 at layer 0 and at pos_embedding,
+    scripts/exp_vit_grad_order.py noise) -- the same amplification its bf16 rounding errors see, which is why the error
+    of the bottom-of-stack gradients sits at 1.4-2.1e-2 depending on what ran before in the process.  A comparison cannot
+    be tighter than the quantity's own reproducibility."""
     from oracle.make_golden import sample_index
     model.train()
-    swin_model.DropPath.forced_masks = iter(torch.from_numpy(mm) for mm in masks) if masks is not None else None
-    try:
-        logits = model(x)
-    finally:
-        swin_model.DropPath.forced_masks = None
-    loss = O.soft_target_ce(logits, tgt, 0.1)
-    loss.backward()
-    assert rel_err(logits.detach(), g["logits_train"]) < TOL
-    assert abs(loss.item() - float(g["loss"])) < TOL * abs(float(g["loss"]))
-    worst = ("", 0.0)
-    for k, p in model.named_parameters():
-        gr = p.grad.detach().float().reshape(-1)
+    runs = []
+    for _ in range(2):
+        model.zero_grad(set_to_none=True)
+        swin_model.DropPath.forced_masks = iter(torch.from_numpy(mm) for mm in masks) if masks is not None else None
+        try:
+            logits = model(x)
+        finally:
+            swin_model.DropPath.forced_masks = None
+        loss = O.soft_target_ce(logits, tgt, 0.1)
+        loss.backward()
+        assert rel_err(logits.detach(), g["logits_train"]) < TOL
+        assert abs(loss.item() - float(g["loss"])) < TOL * abs(float(g["loss"]))
+        runs.append({k: p.grad.detach().float().reshape(-1).clone() for k, p in model.named_parameters()})
+    worst = ("", 0.0, 0.0)
+    for k, gr in runs[0].items():
         n, want = float(gr.double().norm()), float(g[f"gnorm/{k}"])
         assert abs(n - want) <= TOL * max(want, 1e-6), (k, n, want)
         idx = torch.from_numpy(sample_index(k, gr.numel())).cuda()
+        noise = rel_err(runs[1][k][idx], gr[idx])
         e = rel_err(gr[idx], g[f"gsamp/{k}"])
         if f"gfull/{k}" in g:
             e = max(e, rel_err(gr, g[f"gfull/{k}"]))
-        if e > worst[1]:
-            worst = (k, e)
+        assert e < TOL + 2.0 * noise, (k, e, noise)
+        if e - 2.0 * noise > worst[1] - 2.0 * worst[2]:
+            worst = (k, e, noise)
     return worst
 
 
@@ -283,7 +306,7 @@ def test_swin5c_full_size_train_gradients():
     masks = synth_keep_masks(2 * (sum(case["depths"]) - 1), 2, keep=0.7, seed=3)
     worst = _full_size_grad_check(model, g, x, tgt, masks, swin_model)
     print("WORST_GRAD swin5c_full_train", worst)
-    assert worst[1] < TOL, worst
+    assert worst[1] < TOL and worst[2] < 1e-5, worst          # reproducible to fp32 atomics: the plain bound
 
 
 def test_vit3c_full_size_train_gradients():
@@ -297,4 +320,4 @@ def test_vit3c_full_size_train_gradients():
     tgt = torch.from_numpy(synth_targets(2, 3, seed=2)).cuda()
     worst = _full_size_grad_check(model, g, x, tgt, None, swin_model)
     print("WORST_GRAD vit3c_full_train", worst)
-    assert worst[1] < TOL, worst
+    assert worst[1] < TOL + 2.0 * worst[2] and worst[2] < 1e-2, worst
