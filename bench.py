@@ -372,7 +372,8 @@ def config_dict(args, world):
                         f"{'+MixUp+z-score on device' if args.mixup else ''} training step",
             "volume": list(vol), "micro_batch": args.batch, "micro_batches_per_step": args.micro_batches,
             "global_batch": args.batch * args.micro_batches * world, "parallelism": f"dp{world}",
-            "micro_batches_fused": bool(not args.no_fuse_micro and not args.torch_ddp and args.micro_batches > 1),
+            "micro_batches_fused": bool(args.impl == "native" and not args.no_fuse_micro and not args.torch_ddp
+                                        and args.micro_batches > 1),
             "l2": f"per-step inputs ({in_mb:.0f} MB) and activations (GBs) exceed the 126 MB L2; no explicit flush"}
 
 
