@@ -845,6 +845,21 @@ def native_main(args):
         gc.collect()
         be.torch.cuda.empty_cache()
         be.sync_all()
+        # the other half of north_star's path: ViT-3D (ViT-S, vit-3c geometry, 811 tokens, global attention on tcgen05)
+        a4 = argparse.Namespace(**vars(args))
+        a4.model, a4.batch, a4.classes, a4.sam, a4.mixup = "vit", 24, 3, False, False
+        w4 = be.build(a4)
+        m4 = measure(be, w4, a4, max(2, args.steps // 2), 3)
+        extras["vit3c_adamw_ema"] = {
+            "config": config_dict(a4, world), "value": round(m4["value"], 2), "unit": "volumes/s",
+            "ms_per_step": round(m4["ms"] / max(2, args.steps // 2), 3),
+            "e2e": {"value": round(m4["e2e"], 2), "unit": "volumes/s"},
+            "model_tflops_per_gpu": round(3 * FLOP_FWD_PER_VOL["vit"] * a4.batch * a4.micro_batches
+                                          / (m4["ms"] / max(2, args.steps // 2) * 1e-3) / 1e12, 1)}
+        del w4
+        gc.collect()
+        be.torch.cuda.empty_cache()
+        be.sync_all()
         if not args.no_fuse_micro and args.micro_batches > 1 and not args.torch_ddp:
             # the same step with the micro-batches accumulated one forward/backward at a time, as the reference's loop
             # does (train/train_transformer.py:1111-1190): what `micro_batches_fused` buys, stated beside the headline
