@@ -48,6 +48,9 @@ def parse(argv=None):
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference", "reference-cuda"])
     ap.add_argument("--model", default="swin", choices=["swin", "vit"])
+    ap.add_argument("--precision", default=None, choices=["bf16", "f16"],
+                    help="16-bit operand encoding of the kernels (default: VSN_B200_PRECISION or bf16); f16 = the "
+                         "IEEE-half build, stepped through a GradScaler as the reference's fp16 loop")
     ap.add_argument("--batch", type=int, default=None, help="volumes per micro-batch per GPU (BATCH_SIZE: 8 / 24)")
     ap.add_argument("--micro-batches", type=int, default=2, help="accumulation micro-batches per step per GPU")
     ap.add_argument("--classes", type=int, default=3)
@@ -522,8 +525,11 @@ class CudaBackend:
                 from vsn_b200.ddp import GradAllReduce
                 sync = GradAllReduce(model.parameters(), bucket_mb=25.0, buffers=model.buffers())
         graph = not args.no_graph and ddp is None
+        scaler = None
+        if self._lib.PRECISION == "f16":      # half-precision gradients need the reference's loss scaling (:1141-1160)
+            scaler = torch.amp.GradScaler("cuda", init_scale=1024.0, growth_interval=100)
         ts = TrainStep(model, use_sam=args.sam, use_ema=not args.no_ema, ddp_model=ddp, grad_sync=sync, graph=graph,
-                       graph_comm=not args.no_graph_comm, fuse_micro_batches=not args.no_fuse_micro)
+                       graph_comm=not args.no_graph_comm, fuse_micro_batches=not args.no_fuse_micro, scaler=scaler)
         G = args.micro_batches
         vol = VOLUMES[args.model]
         host = [synth_batch(args.batch, args.classes, seed=1234 + self.rank * 100 + i, volume=vol) for i in range(G)]
@@ -879,6 +885,18 @@ def native_main(args):
     # ---- baselines on rank 0 at N = 1 only -------------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.stub:
+        if not args.no_extras and be._lib.PRECISION == "bf16":
+            # the same step in the precision mode (IEEE-half operands, GradScaler): the operand encoding is fixed per
+            # process, so a child process measures it
+            cmd = [sys.executable, os.path.abspath(__file__), "--precision", "f16", "--model", args.model, "--classes",
+                   str(args.classes), "--steps", str(max(2, args.steps // 2)), "--warmup", "3", "--no-extras",
+                   "--no-cpu-baseline", "--no-profile"] + (["--sam"] if args.sam else [])
+            try:
+                r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+                ln = json.loads([x for x in r.stdout.splitlines() if x.startswith("{")][-1])
+                extras["f16_precision_mode"] = {k: ln[k] for k in ("value", "unit", "ms_per_step", "dtype", "e2e", "config")}
+            except Exception as e:      # noqa: BLE001 -- an extras line must not take the headline down
+                extras["f16_precision_mode"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
         if not args.no_extras and args.model == "swin":
             try:
                 extras["swin5c_tta_ensemble_infer"] = tta_ensemble_arm(args, be.dev)
@@ -901,7 +919,7 @@ def native_main(args):
         line = {"metric": f"{args.model}3d_train_volumes_per_s", "value": round(m["value"], 2), "unit": "volumes/s",
                 "n_gpus": world, "steps": args.steps, "warmup": warmup,
                 "ms_per_step": round(m["ms"] / args.steps, 3), "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config_dict(args, world),
+                "vs_baseline": None, "dtype": "bf16" if args.stub else be._lib.PRECISION, "data": "synthetic", "config": config_dict(args, world),
                 "clocks": clocks, "replicas_in_sync": in_sync, "gpu_launches": int(m["launches"]),
                 "cuda_graph": bool(not args.no_graph and not args.torch_ddp),
                 "host_enqueue_ms_per_step": round(m["host_ms"], 3),
@@ -920,6 +938,8 @@ def wl_h2d(args):
 
 def main(argv=None):
     args = parse(argv)
+    if args.precision is not None:
+        os.environ["VSN_B200_PRECISION"] = args.precision     # read once, when vsn_b200._lib is imported
     if args.impl != "native":
         return reference_main(args)
     return native_main(args)

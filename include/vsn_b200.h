@@ -13,7 +13,10 @@
  *     no C++ exception crosses the boundary;
  *   - re-entrant and thread-safe (forward runs on the caller's thread, backward on the autograd thread);
  *   - sm_100a only: vsn_check_device() fails on anything else and there is no fallback path;
- *   - "bf16" is the 16-bit brain float; fp32 is IEEE binary32.
+ *   - "bf16" is the 16-bit brain float; fp32 is IEEE binary32.  The precision build libvsn_b200_f16.so (same
+ *     sources, -DVSN_F16) exports the same entry points with every "bf16" buffer holding IEEE binary16 instead --
+ *     TF32's 11 significant bits, the dtype of the reference's autocast path (train/train_transformer.py:1141-1160);
+ *     vsn_precision() tells the two apart.
  */
 #ifndef VSN_B200_H_
 #define VSN_B200_H_
@@ -24,6 +27,8 @@ extern "C" {
 
 /* ---- library ------------------------------------------------------------------------------- */
 int vsn_version(void);
+/* 0: the 16-bit buffers are bfloat16 (default build); 1: IEEE binary16 (libvsn_b200_f16.so) */
+int vsn_precision(void);
 const char* vsn_last_error(void);
 int vsn_check_device(void);
 /* kernel launches issued by the library since it was loaded (bench.py's gpu_launches counter) */

@@ -35,3 +35,13 @@ def test_binding_matches_header():
     assert bound == set(header_symbols())
     lib = _lib.load()
     assert lib.vsn_version() >= 100
+
+
+def test_precision_build_exports_the_same_abi():
+    """libvsn_b200_f16.so (-DVSN_F16: IEEE-half operands) is the same ABI; each build names its own encoding."""
+    f16 = os.path.join(os.path.dirname(_lib.LIB_PATH), "libvsn_b200_f16.so")
+    assert os.path.exists(f16), "build the library first: python __graft_entry__.py build"
+    lib = ctypes.CDLL(f16)
+    missing = [s for s in header_symbols() if not hasattr(lib, s)]
+    assert not missing, missing
+    assert lib.vsn_precision() == 1 and _lib.load().vsn_precision() == (0 if _lib.PRECISION == "bf16" else 1)

@@ -251,7 +251,7 @@ def test_train_step_fused_adamw_equals_torch_adamw():
     case = cases.SWIN_CASES["swin_small_even"]
     for use_sam in (False, True):
         finals = []
-        for fused in (True, False):
+        for fused in (True, False, True):
             torch.manual_seed(0)
             m = swin_model.SwinTransformer(**cases.swin_ctor_kwargs(case)).cuda()
             init = [p.detach().clone() for p in m.parameters()]
@@ -262,13 +262,80 @@ def test_train_step_fused_adamw_equals_torch_adamw():
                             torch.softmax(torch.randn(case["input"][0], case["num_classes"], generator=g), -1).cuda())
                            for _ in range(2)]
                 ts.step(batches)
-            finals.append([p.detach() - p0 for p, p0 in zip(m.parameters(), init)])
-        # the gradient kernels accumulate with atomics (summation order varies run to run), and AdamW turns a sign flip
-        # of a noise-level gradient into a full +-lr move: compare the UPDATES in the L2 sense
-        num = sum(float(((x - y) ** 2).sum()) for x, y in zip(*finals))
-        den = sum(float((y ** 2).sum()) for y in finals[1])
-        # (measured 1.9e-3: a weight that differs in its last fp32 bit can round to the other bf16 neighbour for step 2)
-        assert den > 0 and (num / den) ** 0.5 < 1e-2, (use_sam, (num / den) ** 0.5)
+            upd = []
+            for (k, p), p0 in zip(m.named_parameters(), init):
+                d = p.detach() - p0
+                if k.endswith("attn.qkv.bias"):
+                    # the key bias has no gradient in exact arithmetic: the kernels deliver summation round-off whose
+                    # sign follows the order of the fp32 atomics, and Adam moves every entry by +-lr whichever sign it
+                    # has (see test_model_gpu.py: graph-vs-eager comparison).  Bound that third, compare q and v.
+                    C = d.numel() // 3
+                    assert float(d[C:2 * C].abs().max()) <= 2 * 1e-3 * 1.01, k
+                    d = torch.cat([d[:C], d[2 * C:]])
+                upd.append(d)
+            finals.append(upd)
+
+        def dist(a, b):
+            num = sum(float(((x - y) ** 2).sum()) for x, y in zip(a, b))
+            den = sum(float((y ** 2).sum()) for y in b)
+            assert den > 0
+            return (num / den) ** 0.5
+        # The gradient kernels accumulate with atomics (summation order varies run to run); AdamW turns a sign flip of a
+        # noise-level gradient into a full +-lr move, and under SAM a last-bit difference of the first gradient moves the
+        # perturbed weights across bf16 rounding boundaries for the second pass.  The step is therefore only
+        # reproducible to `noise` (the SAME fused configuration run twice: measured 2e-3 plain, 1.3-1.5e-2 under SAM);
+        # the fused and the torch optimiser must agree to that.  Element-wise equality with torch.optim.AdamW on
+        # identical gradients is test_fused_adamw_matches_torch_adamw_and_clears_gradients's job (1e-6).
+        noise = dist(finals[2], finals[0])
+        assert dist(finals[0], finals[1]) < 1e-2 + 2.0 * noise, (use_sam, dist(finals[0], finals[1]), noise)
+        assert noise < 5e-2, (use_sam, noise)
+
+
+@pytest.mark.parametrize("use_sam", [False, True])
+def test_train_step_under_grad_scaler(use_sam):
+    """TrainStep(scaler=GradScaler): the reference's fp16 loop order (train/train_transformer.py:1141-1160,1194-1232).
+    A power-of-two loss scale changes nothing but the exponent of the gradients, so the step equals the unscaled one (to
+    the run-to-run noise of the atomics); non-finite gradients skip the update, halve the scale and still leave a
+    cleared gradient arena for the next pass."""
+    import vsn_b200  # noqa: F401
+    from vsn_b200 import swin_model, train
+    from oracle import cases
+    case = cases.SWIN_CASES["swin_small_even"]
+    g = torch.Generator().manual_seed(7)
+    batches = [(torch.randn(*case["input"], generator=g).cuda().half(),
+                torch.softmax(torch.randn(case["input"][0], case["num_classes"], generator=g), -1).cuda()) for _ in range(2)]
+    grads = []
+    for scale in (None, 1024.0):
+        torch.manual_seed(0)
+        m = swin_model.SwinTransformer(**cases.swin_ctor_kwargs(case)).cuda()
+        sc = None if scale is None else torch.amp.GradScaler("cuda", init_scale=scale, growth_interval=1000)
+        ts = train.TrainStep(m, lr=1e-3, use_sam=use_sam, use_ema=False, scaler=sc)
+        ts._accumulate(batches)
+        grads.append([p.grad.detach().clone() / (scale or 1.0) for p in m.parameters()])
+        ts._zero_grad()
+        w0 = [p.detach().clone() for p in m.parameters()]
+        ts.step(batches)
+        assert all(bool(torch.isfinite(p).all()) for p in m.parameters())
+        assert sum(float((p.detach() - q).abs().max()) > 0 for p, q in zip(m.parameters(), w0)) > 0.9 * len(w0)
+        assert all(float(p.grad.abs().max()) == 0.0 for p in m.parameters())          # cleared for the next pass
+        if sc is not None:
+            assert sc.get_scale() == scale
+        ts.grad_sync.remove()
+    for a, b in zip(*grads):
+        assert float((a - b).norm()) <= 1e-3 * float(b.norm()) + 1e-9
+    # non-finite gradients (an inf voxel in one volume: bf16 has fp32's range, a large scale alone does not overflow)
+    torch.manual_seed(0)
+    m = swin_model.SwinTransformer(**cases.swin_ctor_kwargs(case)).cuda()
+    sc = torch.amp.GradScaler("cuda", init_scale=2.0 ** 126)
+    ts = train.TrainStep(m, lr=1e-3, use_sam=use_sam, use_ema=False, scaler=sc)
+    w0 = [p.detach().clone() for p in m.parameters()]
+    bad = [(x.clone(), y) for x, y in batches]
+    bad[1][0].view(-1)[12345] = float("inf")
+    ts.step(bad)
+    assert all(bool((p.detach() == q).all()) for p, q in zip(m.parameters(), w0))       # skipped
+    assert all(float(p.grad.abs().max()) == 0.0 for p in m.parameters())
+    assert sc.get_scale() < 2.0 ** 126
+    ts.grad_sync.remove()
 
 
 def test_fused_micro_batches_give_the_accumulated_gradient():

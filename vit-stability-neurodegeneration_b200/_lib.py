@@ -8,13 +8,30 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvsn_b200.so")
+# Precision of the 16-bit operands, fixed for the life of the process (one library, one activation dtype):
+#   "bf16" (default)  libvsn_b200.so      bfloat16 operands, fp32 accumulation: logits / gradients within 2e-2
+#   "f16"             libvsn_b200_f16.so  the same kernels built with -DVSN_F16: IEEE-half operands, i.e. TF32's
+#                     11 significant bits with fp32 accumulation -- the precision mode of north_star's tighter
+#                     tolerance and the dtype the reference trains in (autocast(float16) + GradScaler,
+#                     train/train_transformer.py:1141-1160); gradients need the usual loss scale.
+PRECISION = os.environ.get("VSN_B200_PRECISION", "bf16").lower()
+if PRECISION not in ("bf16", "f16"):
+    raise RuntimeError(f"VSN_B200_PRECISION must be 'bf16' or 'f16', got {PRECISION!r}")
+LIB_PATH = os.path.join(_HERE, "libvsn_b200.so" if PRECISION == "bf16" else "libvsn_b200_f16.so")
+
+
+def act_dtype():
+    """torch dtype of the 16-bit activations / operands this process computes in."""
+    import torch
+    return torch.bfloat16 if PRECISION == "bf16" else torch.float16
+
 
 _p, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 
 # name -> argtypes (restype is int unless noted)
 SIGNATURES = {
     "vsn_version": [],
+    "vsn_precision": [],
     "vsn_check_device": [],
     "vsn_gemm_bf16": [_p, _ll, _i, _p, _ll, _i, _i, _i, _i, _p, _ll, _i, _p, _i, _p, _ll, _p, _ll, _p, _i, _f, _i, _p, _p],
     "vsn_layernorm_fwd": [_p, _ll, _p, _p, _p, _ll, _i, _p, _p, _ll, _i, _f, _p],
@@ -68,6 +85,9 @@ def load() -> C.CDLL:
         lib.vsn_launch_count.restype = C.c_longlong
         lib.vsn_last_error.argtypes = []
         lib.vsn_last_error.restype = C.c_char_p
+        if lib.vsn_precision() != (0 if PRECISION == "bf16" else 1):
+            raise RuntimeError(f"{LIB_PATH} was not built for VSN_B200_PRECISION={PRECISION}: rebuild it "
+                               "(python __graft_entry__.py build)")
         _lib = lib
     return _lib
 

@@ -41,6 +41,16 @@ extern "C" const char* vsn_last_error() { return g_err; }
 
 extern "C" int vsn_version() { return 100; }
 
+// 16-bit operand encoding this build computes in: 0 = bfloat16 (libvsn_b200.so), 1 = IEEE half (libvsn_b200_f16.so,
+// the same sources compiled with -DVSN_F16).  The binding checks it against the dtype it allocates.
+extern "C" int vsn_precision() {
+#ifdef VSN_F16
+  return 1;
+#else
+  return 0;
+#endif
+}
+
 // 0 when the current device can run this library (compute capability 10.x); the Python side
 // refuses to continue otherwise -- there is no fallback path.
 extern "C" int vsn_check_device() {

@@ -9,6 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB = os.path.join(PKG, "libvsn_b200.so")
+LIB_F16 = os.path.join(PKG, "libvsn_b200_f16.so")   # the same sources with -DVSN_F16: IEEE-half operands (precision mode)
 SOURCES = ["api.cu", "gemm_tc.cu", "attn.cu", "wattn_tc.cu", "dattn_tc.cu", "norm.cu", "layout.cu", "optim.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math" if False else "-DVSN_B200=1"]
@@ -21,20 +22,24 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
-def needs_build() -> bool:
-    if not os.path.exists(LIB):
+def needs_build(lib: str = LIB) -> bool:
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
+    t = os.path.getmtime(lib)
     deps = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".cu", ".cuh"))]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False, extra_flags=(), only=None) -> str:
-    """extra_flags / only (source names) serve measurement builds, e.g. `-DVSN_MBAR_HINT_NS=0` for wattn_tc.cu."""
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, extra_flags=(), only=None, f16: bool = False) -> str:
+    """extra_flags / only (source names) serve measurement builds, e.g. `-DVSN_MBAR_HINT_NS=0` for wattn_tc.cu.
+    f16=True builds the half-operand variant (libvsn_b200_f16.so) from the same sources."""
+    LIB = LIB_F16 if f16 else globals()["LIB"]
+    if not force and not needs_build(LIB):
         return LIB
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build_f16" if f16 else "build")
+    if f16:
+        extra_flags = [*extra_flags, "-DVSN_F16=1"]
     os.makedirs(objdir, exist_ok=True)
 
     def compile_one(src):
@@ -64,4 +69,6 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), only=None)
 if __name__ == "__main__":
     extra = [a for a in sys.argv[1:] if a.startswith("-D")]
     only = [a[len("--only="):] for a in sys.argv[1:] if a.startswith("--only=")] or None
-    print(build(force="--force" in sys.argv or bool(extra), verbose="-v" in sys.argv, extra_flags=extra, only=only))
+    variants = [True] if "--f16-only" in sys.argv else ([False] if "--bf16-only" in sys.argv else [False, True])
+    for f16 in variants:
+        print(build(force="--force" in sys.argv or bool(extra), verbose="-v" in sys.argv, extra_flags=extra, only=only, f16=f16))

@@ -162,7 +162,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& pa, int row, int 
       for (int j = 0; j < 4; ++j)
         *reinterpret_cast<uint4*>(ap + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
     } else {
-      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { ap[j] = __float2bfloat16(f[j]); }
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { ap[j] = f2b(f[j]); }
     }
     if (p.gelu_fp32 & 1) {
 #pragma unroll
@@ -207,7 +207,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& pa, int row, int 
         }
       }
     } else {
-      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { f[j] *= gelu_erf_grad<false>(__bfloat162float(ap[j])); }
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { f[j] *= gelu_erf_grad<false>(b2f(ap[j])); }
     }
   }
   if (rs != 1.0f) {
@@ -251,7 +251,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& pa, int row, int 
         *reinterpret_cast<uint4*>(op + j) = u;
       }
     } else {
-      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { op[j] = __float2bfloat16(f[j]); }
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < nvalid) { op[j] = f2b(f[j]); }
     }
   } else if (m.out_kind() == 1) {
     float* op = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + n;
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
     else tc::tmem_alloc(tmem_slot, C::TMEM_COLS);
   }
   if (p.rowsum != nullptr) {
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) reinterpret_cast<uint32_t*>(ones_s)[i] = 0x3F803F80u;   // bf16 1.0 pairs
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) reinterpret_cast<uint32_t*>(ones_s)[i] = VSN_ONE_PAIR;   // 1.0 pairs
     tc::fence_proxy_async();
   }
   tc::fence_before_sync();
@@ -564,7 +564,7 @@ int make_tmap_2d(CUtensorMap* map, const void* base, long long dim0, long long d
   cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 2};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(box0), static_cast<cuuint32_t>(box1)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+  CUresult r = fn(map, VSN_TMAP_DTYPE, 2, const_cast<void*>(base), gdim, gstr, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VSN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (dims %lld x %lld ld %lld box %d x %d)",

@@ -12,10 +12,10 @@ __device__ __forceinline__ float ld_as_float<float>(const float* p) { return *p;
 template <>
 __device__ __forceinline__ float ld_as_float<__half>(const __half* p) { return __half2float(*p); }
 template <>
-__device__ __forceinline__ float ld_as_float<bf16>(const bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ float ld_as_float<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 
 __device__ __forceinline__ void st_from_float(float* p, float v) { *p = v; }
-__device__ __forceinline__ void st_from_float(bf16* p, float v) { *p = __float2bfloat16(v); }
+__device__ __forceinline__ void st_from_float(bf16* p, float v) { *p = f2b(v); }
 
 // out[(b,d,h,w), (i,j,k)] = vol[b, d*pd+i, h*ph+j, w*pw+k]  (zero beyond D,H,W).
 // PatchEmbed3D's pad + Conv3d(k=s=patch) operand (models/swin_transformer_3d.py:532-539) and the ViT
@@ -65,10 +65,10 @@ __device__ __forceinline__ void load4<__half>(const __half* p, float* v) {
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
 template <>
-__device__ __forceinline__ void load4<bf16>(const bf16* p, float* v) {
+__device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float* v) {
   const uint2 u = *reinterpret_cast<const uint2*>(p);
-  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
-  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xFFFF0000u);
+  v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xFFFF0000u);
 }
 
 template <typename InT>
@@ -184,7 +184,7 @@ __global__ void cast_rows_kernel(const float* __restrict__ src, bf16* __restrict
 __global__ void cast_flat_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
-    dst[i] = __float2bfloat16(src[i]);
+    dst[i] = f2b(src[i]);
 }
 
 // out[b, c] = mean_t x[b, t, c]  (AdaptiveAvgPool3d(1), models/swin_transformer_3d.py:696) and its gradient
@@ -479,7 +479,7 @@ extern "C" int vsn_patch_gather(const void* vol, int in_dtype, void* out, int ou
     bf16* o = reinterpret_cast<bf16*>(out);
     if (in_dtype == 0) patch_gather444_kernel<float><<<g4, 256, 0, s>>>(reinterpret_cast<const float*>(vol), o, B, D, H, W, gd, gh, gw);
     else if (in_dtype == 1) patch_gather444_kernel<__half><<<g4, 256, 0, s>>>(reinterpret_cast<const __half*>(vol), o, B, D, H, W, gd, gh, gw);
-    else patch_gather444_kernel<bf16><<<g4, 256, 0, s>>>(reinterpret_cast<const bf16*>(vol), o, B, D, H, W, gd, gh, gw);
+    else patch_gather444_kernel<__nv_bfloat16><<<g4, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(vol), o, B, D, H, W, gd, gh, gw);
     VSN_LAUNCH_CHECK();
     return 0;
   }
@@ -491,8 +491,8 @@ extern "C" int vsn_patch_gather(const void* vol, int in_dtype, void* out, int ou
   else if (in_dtype == 0) VSN_PG(float, float);
   else if (in_dtype == 1 && out_bf16) VSN_PG(__half, bf16);
   else if (in_dtype == 1) VSN_PG(__half, float);
-  else if (in_dtype == 2 && out_bf16) VSN_PG(bf16, bf16);
-  else if (in_dtype == 2) VSN_PG(bf16, float);
+  else if (in_dtype == 2 && out_bf16) VSN_PG(__nv_bfloat16, bf16);
+  else if (in_dtype == 2) VSN_PG(__nv_bfloat16, float);
   else { vsn_set_error("vsn_patch_gather: bad in_dtype %d", in_dtype); return 1; }
 #undef VSN_PG
   VSN_LAUNCH_CHECK();

@@ -14,10 +14,10 @@ __device__ __forceinline__ float to_f(T v);
 template <>
 __device__ __forceinline__ float to_f<float>(float v) { return v; }
 template <>
-__device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_f<bf16>(bf16 v) { return b2f(v); }
 
 __device__ __forceinline__ void store_out(float* p, float v) { *p = v; }
-__device__ __forceinline__ void store_out(bf16* p, float v) { *p = __float2bfloat16(v); }
+__device__ __forceinline__ void store_out(bf16* p, float v) { *p = f2b(v); }
 
 // One warp per row.  Rows up to 1024 wide are held in registers (one HBM read); wider rows are
 // re-read from L1/L2 for the second and third sweep.

@@ -216,9 +216,13 @@ __global__ void __launch_bounds__(MT_THREADS) mt_adamw_kernel(const long long* p
   int tensor; long long off, n;
   if (!chunk_span(tab, tensor, off, n)) return;
   const float bc1 = ctl[0], bc2s = ctl[1], inv_scale = ctl[3];
-  if (ctl[2] != 0.f) return;                              // found_inf: the whole step is skipped (gradients kept)
-  float* p = reinterpret_cast<float*>(p_ptrs[tensor]) + off;
   float* g = reinterpret_cast<float*>(g_ptrs[tensor]) + off;
+  if (ctl[2] != 0.f) {                                    // found_inf: the whole step is skipped; the fused clear still
+    if (zero_grad)                                        // happens (the next pass accumulates into these buffers)
+      for (long long i = threadIdx.x; i < n; i += MT_THREADS) g[i] = 0.f;
+    return;
+  }
+  float* p = reinterpret_cast<float*>(p_ptrs[tensor]) + off;
   float* m = reinterpret_cast<float*>(m_ptrs[tensor]) + off;
   float* v = reinterpret_cast<float*>(v_ptrs[tensor]) + off;
   const float decay = 1.f - lr * wd[tensor], step_size = lr / bc1;   // omb1/omb2 = 1 - beta, rounded from double like torch's
@@ -281,7 +285,7 @@ __global__ void __launch_bounds__(MT_THREADS) mt_cast_bf16_kernel(const long lon
     }
     done = n4 << 2;
   }
-  for (long long i = done + threadIdx.x; i < n; i += MT_THREADS) d[i] = __float2bfloat16(s[i]);
+  for (long long i = done + threadIdx.x; i < n; i += MT_THREADS) d[i] = f2b(s[i]);
 }
 
 }  // namespace

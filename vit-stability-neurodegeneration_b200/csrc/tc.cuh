@@ -321,9 +321,14 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_
   d |= static_cast<uint64_t>(2) << 61;  // SWIZZLE_128B
   return d;
 }
-// Instruction descriptor for kind::f16 with bf16 inputs, fp32 accumulation.
+// Instruction descriptor for kind::f16 with bf16 (or, under -DVSN_F16, half) inputs, fp32 accumulation.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+#ifdef VSN_F16
+  constexpr uint32_t ab_format = 0u;                       // A and B are IEEE half (formats 0 / 0)
+#else
+  constexpr uint32_t ab_format = (1u << 7) | (1u << 10);   // A and B are bfloat16 (formats 1 / 1)
+#endif
+  return (1u << 4) | ab_format | (static_cast<uint32_t>(a_mn_major) << 15) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }

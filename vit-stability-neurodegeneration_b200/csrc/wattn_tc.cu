@@ -32,7 +32,11 @@ constexpr int STAGE_BYTES = 3 * TILE_BYTES;   // Q | K | V (forward kernel; the 
 // (a single value e for both sides cannot do better than e^2 = 564.06 -> 99.7 or 576 -> 101.8 nats).
 constexpr float REGION_Q = 9.3125f;            // bf16 0x4115
 constexpr float REGION_K = 60.75f;             // bf16 0x4273
+#ifdef VSN_F16
+constexpr uint32_t REGION_Q_BITS = 0x48A8u, REGION_K_BITS = 0x5398u;   // the same two values as IEEE half
+#else
 constexpr uint32_t REGION_Q_BITS = 0x4115u, REGION_K_BITS = 0x4273u;
+#endif
 constexpr float REGION_SQ = REGION_Q * REGION_K;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float MASK_L2E = -100.0f * LOG2E;
@@ -162,7 +166,7 @@ __device__ __forceinline__ void add_bias(uint32_t* x, const uint8_t* tab, int ro
     for (int wj = 0; wj < WW; ++wj) {
       const int k = kr * WW + wj - PART * 64;
       if (k < 0 || k >= 64) continue;
-      const float b = (wj & 1) ? __uint_as_float(bw[wj >> 1] & 0xFFFF0000u) : __uint_as_float(bw[wj >> 1] << 16);
+      const float b = (wj & 1) ? bf16hi(bw[wj >> 1]) : bf16lo(bw[wj >> 1]);
       x[k] = __float_as_uint(fmaf(__uint_as_float(x[k]), cscale, b));
     }
   }
@@ -561,14 +565,14 @@ __device__ __forceinline__ void add_bias_t16(float* x, const uint8_t* tab, int r
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
     const int r = (W0 + k) / WW, wi = (W0 + k) % WW;
-    const float b = (wi & 1) ? __uint_as_float(bw[r][wi >> 1] & 0xFFFF0000u) : __uint_as_float(bw[r][wi >> 1] << 16);
+    const float b = (wi & 1) ? bf16hi(bw[r][wi >> 1]) : bf16lo(bw[r][wi >> 1]);
     x[k] = fmaf(x[k], cscale, b);
   }
 }
 
 // 8 bf16 (16 bytes) added to global memory with one REDG.BF16x8
 __device__ __forceinline__ void red_add_bf16x8(bf16* addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
+  asm volatile("red.global.add.noftz.v4." VSN_T16 "x2 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
                : "memory");
 }
 
@@ -639,7 +643,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) wattn_bwd_kernel(const WinAttn
   for (int i = threadIdx.x; i < 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(ident)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
   if (threadIdx.x < 16)   // I16 as a K-major [16 rows][32] tile (64-byte swizzle), element (n, n) = 1
-    *reinterpret_cast<bf16*>(ident + swz64(threadIdx.x, threadIdx.x >> 3) + (threadIdx.x & 7) * 2) = __float2bfloat16(1.0f);
+    *reinterpret_cast<bf16*>(ident + swz64(threadIdx.x, threadIdx.x >> 3) + (threadIdx.x & 7) * 2) = f2b(1.0f);
   for (int i = threadIdx.x; i < 2 * (NP - N); i += blockDim.x) {
     const int st = i / (NP - N), q = N + i % (NP - N);
     reinterpret_cast<float*>(stages + st * BWD_STAGE_BYTES + 49152)[q] = 30000.f;   // lse2 pad -> P = 0

@@ -11,7 +11,7 @@ import torch
 
 from . import _lib
 
-BF16 = torch.bfloat16
+BF16 = _lib.act_dtype()   # the 16-bit operand dtype of this process (bfloat16, or float16 under VSN_B200_PRECISION=f16)
 F32 = torch.float32
 
 
@@ -202,7 +202,7 @@ def attn_bwd(qkv, out, dout, lse, heads: int, hd: int, *, S: int, N: int, scale:
 
 
 # ------------------------------------------------------------------ layout kernels
-_IN_DTYPE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+_IN_DTYPE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}   # volume dtypes (input side), not BF16
 
 
 def patch_gather(vol: torch.Tensor, patch: Sequence[int], *, out_dtype=BF16) -> torch.Tensor:

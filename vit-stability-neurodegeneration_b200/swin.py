@@ -15,7 +15,7 @@ import torch
 
 from . import ops
 
-F32, BF16 = torch.float32, torch.bfloat16
+F32, BF16 = torch.float32, ops.BF16
 
 # dtype of the two activation gradients that feed the LayerNorm backward kernels (outputs of the qkv / fc1 dgrad GEMMs).
 # fp32 keeps the LayerNorm parameter gradients and the residual-stream gradient free of one bf16 rounding.

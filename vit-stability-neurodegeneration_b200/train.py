@@ -57,6 +57,12 @@ class TrainStep:
     grad_sync   a `ddp.GradAllReduce` over `model.parameters()` built by the caller (N > 1); without one the step
                 builds its own arena (world size 1: nothing is exchanged)
     graph       capture forward + loss + backward of a micro-batch in a CUDA graph and replay it
+    scaler      a torch.amp.GradScaler: the loss is scaled before backward and the optimiser steps through it, call for call
+                as the reference's fp16 loop does (train/train_transformer.py:1141-1160,1194-1232: `scale(loss).backward()`,
+                `scaler.step` / `update`; under SAM `unscale_` -> first_step -> `update` -> second pass ->
+                `second_step(scaler=...)`).  Needed in the f16 precision mode (VSN_B200_PRECISION=f16), whose half-precision
+                activation gradients underflow without a loss scale; FusedAdamW takes the unscale and the inf check into
+                its own pass.
     graph_comm  (N > 1, graph mode) capture a second graph for the LAST micro-batch of a pass with the bucket
                 all-reduces inside it: NCCL runs on the communication stream as a forked branch of the graph, each
                 bucket as soon as backward has completed it, so the exchange overlaps the rest of backward exactly as
@@ -66,7 +72,8 @@ class TrainStep:
     def __init__(self, model: torch.nn.Module, *, lr: float = 1e-4, weight_decay: float = 0.05, use_sam: bool = False,
                  sam_rho: float = 0.05, use_ema: bool = True, ema_decay: float = 0.999, smoothing: float = 0.1,
                  ddp_model: Optional[torch.nn.Module] = None, grad_sync: Optional[GradAllReduce] = None,
-                 graph: bool = False, graph_comm: bool = True, fused_adamw: bool = True, fuse_micro_batches: bool = False):
+                 graph: bool = False, graph_comm: bool = True, fused_adamw: bool = True, fuse_micro_batches: bool = False,
+                 scaler: Optional["torch.amp.GradScaler"] = None):
         self.module = model                       # the bare module (EMA / parameters)
         self.model = ddp_model if ddp_model is not None else model   # what forward is called on
         self.autograd_grads = ddp_model is not None
@@ -87,6 +94,7 @@ class TrainStep:
         self.fused_adamw = fused_adamw
         self.fuse_micro_batches = fuse_micro_batches and ddp_model is None
         self.use_sam = use_sam
+        self.scaler = scaler
         self.ema = EMAModel(model=model, decay=ema_decay) if use_ema else None
         self.smoothing = smoothing
         self.use_graph = graph
@@ -101,7 +109,7 @@ class TrainStep:
     # ------------------------------------------------------------------ one micro-batch
     def _fwd_bwd(self, x: torch.Tensor, y: torch.Tensor, n: int) -> torch.Tensor:
         loss = soft_target_ce(self.model(x), y, self.smoothing) / n
-        loss.backward()
+        (loss if self.scaler is None else self.scaler.scale(loss)).backward()
         return loss.detach()
 
     def _capture(self, x: torch.Tensor, y: torch.Tensor, n: int) -> None:
@@ -234,7 +242,24 @@ class TrainStep:
     def step(self, batches: Sequence[Tuple[torch.Tensor, torch.Tensor]]) -> torch.Tensor:
         """One optimiser step over the given micro-batches; returns the (device) loss of the first pass."""
         loss = self._accumulate(batches)
-        if self.use_sam:
+        if self.scaler is not None:
+            sc = self.scaler
+            if self.use_sam:
+                sc.unscale_(self.opt.base_optimizer)
+                self.opt.first_step(zero_grad=False)
+                self._zero_grad()
+                sc.update()
+                self._accumulate(batches)
+                self.opt.second_step(zero_grad=False, scaler=sc)       # restore, scaler.step(base), scaler.update()
+                self._zero_grad()
+            else:
+                if self.fused_adamw:
+                    sc.step(self.opt, zero_grad=True)
+                else:
+                    sc.step(self.opt)
+                    self._zero_grad()
+                sc.update()
+        elif self.use_sam:
             self.opt.first_step(zero_grad=False)
             self._zero_grad()
             self._accumulate(batches)

@@ -7,7 +7,7 @@ import torch
 from . import ops
 from .swin import GradSink, _contig_f32, zeros_like_shapes
 
-F32, BF16 = torch.float32, torch.bfloat16
+F32, BF16 = torch.float32, ops.BF16
 
 
 class ViTEmbedFn(torch.autograd.Function):
