@@ -355,6 +355,39 @@ def test_grid_copy_and_merge_gather_bit_exact():
     assert float(dx.abs().sum()) == float(x.abs().sum())
 
 
+@pytest.mark.parametrize("C,real,padded", [(96, (6, 7, 5), (6, 7, 5)), (96, (7, 8, 5), (12, 14, 6)),
+                                           (192, (9, 11, 9), (9, 11, 9)), (192, (4, 3, 6), (6, 7, 6))])
+def test_merge_gather_fused_into_layernorm(C, real, padded):
+    """vsn_merge_ln_fwd / _bwd (PatchMerging's gather inside its LayerNorm, models/swin_transformer_3d.py:553-572)
+    against the two-kernel composition merge_gather + layernorm: the forward bit for bit (same element-to-lane map and
+    summation order), the backward to the order of the dgamma / dbeta atomics; odd extents (zero neighbours) and a
+    padded stage grid (tokens the backward must leave zero) included."""
+    ops = _ops()
+    B = 2
+    x = _rand(B * real[0] * real[1] * real[2], C, seed=1)
+    xp = ops.grid_copy(x, real, padded, B, C) if real != padded else x
+    gamma, beta = 1.0 + 0.1 * _rand(8 * C, seed=2), 0.1 * _rand(8 * C, seed=3)
+    xg = ops.merge_gather(xp, padded, real, B, C)
+    y_ref, mean_ref, rstd_ref = ops.layernorm_fwd(xg, gamma, beta)
+    y, mean, rstd = ops.merge_ln_fwd(xp, gamma, beta, padded, real, B, C)
+    if C == 96:       # LayerNorm(768) takes the register-resident kernel with the same lane map: bit for bit
+        assert torch.equal(y, y_ref) and torch.equal(mean, mean_ref) and torch.equal(rstd, rstd_ref)
+    else:             # LayerNorm(1536) takes the generic kernel (another summation order): fp32 round-off
+        assert rel_err(mean, mean_ref) < 1e-5 and rel_err(rstd, rstd_ref) < 1e-6
+        assert rel_err(y.float(), y_ref.float()) < 1e-3
+    dy = _rand(*y.shape, seed=4).to(y.dtype)
+    dg_ref, db_ref = torch.zeros(8 * C, device="cuda"), torch.zeros(8 * C, device="cuda")
+    dxg, _ = ops.layernorm_bwd(dy, xg, mean_ref, rstd_ref, gamma, dgamma=dg_ref, dbeta=db_ref)
+    dx_ref = ops.merge_scatter(dxg, padded, real, B, C)
+    dg, db = torch.ones(8 * C, device="cuda"), torch.ones(8 * C, device="cuda")        # accumulate (+=)
+    dx = ops.merge_ln_bwd(dy, xp, mean, rstd, gamma, dg, db, padded, real, B, C)
+    assert rel_err(dx, dx_ref) < 1e-6
+    pad_mask = torch.ones(B, *padded, 1, device="cuda", dtype=torch.bool)
+    pad_mask[:, :real[0], :real[1], :real[2]] = False
+    assert float((dx.reshape(B, *padded, C) * pad_mask).abs().max()) == 0.0
+    assert rel_err(dg - 1.0, dg_ref) < 1e-5 and rel_err(db - 1.0, db_ref) < 1e-5
+
+
 def test_head_and_token_mean():
     ops = _ops()
     B, T, F_, K = 3, 150, 768, 5

@@ -16,8 +16,9 @@ HARNESS = os.path.join(ROOT, "scripts", "run_reference_trainer.py")
 HAVE_REF = os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "train"))
 
 
-def _run(*args, timeout=900):
-    r = subprocess.run([sys.executable, HARNESS, *args], capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+def _run(*args, timeout=900, env=None):
+    r = subprocess.run([sys.executable, HARNESS, *args], capture_output=True, text=True, timeout=timeout, cwd=ROOT,
+                       env=None if env is None else dict(os.environ, **env))
     assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
     return r.stdout + r.stderr
 
@@ -32,4 +33,19 @@ def test_unmodified_trainer_runs_on_the_dropin_and_checkpoints_interchange(arch,
     log = _run("--arch", arch, "--steps", "6", "--out", out, "--resume")
     assert "Step 6" in log
     log = _run("--arch", arch, "--out", out, "--compare")
+    assert "loaded strictly into the reference" in log
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="baseline/_ref not installed")
+def test_unmodified_trainer_runs_in_the_f16_precision_mode(tmp_path):
+    """VSN_B200_PRECISION=f16: the trainer's own fp16 loop (autocast + GradScaler, SAM's unscale_ / second_step(scaler))
+    drives the IEEE-half build of the kernels; the checkpoint still interchanges with the reference model."""
+    out = str(tmp_path / "run16")
+    env = {"VSN_B200_PRECISION": "f16"}
+    log = _run("--arch", "swin", "--steps", "4", "--out", out, env=env)
+    assert "Using SAM optimizer" in log and "Gradient Scaler active" in log and "Step 4" in log and "Checkpoint saved" in log
+    import re
+    vals = [float(v) for v in re.findall(r"Val: loss ([0-9.naninf]+),", log)]
+    assert vals and all(v == v and v < 10.0 for v in vals), vals          # finite validation losses
+    log = _run("--arch", "swin", "--out", out, "--compare", env=env)
     assert "loaded strictly into the reference" in log

@@ -363,6 +363,186 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_fast_kernel(const DyT* _
   }
 }
 
+// ---- PatchMerging: gather of the 2x2x2 neighbours fused into LayerNorm(8C) ------------------------------------
+// (models/swin_transformer_3d.py:553-572: x0..x7 concatenated in the order (od,oh,ow) = (0,0,0),(1,0,0),(0,1,0),
+// (0,0,1),(1,1,0),(1,0,1),(0,1,1),(1,1,1), positions beyond the real grid read as zero, then norm(8C), then the
+// reduction Linear.)  The merged row never exists in HBM: a warp owns one merged row, lane l holds the float4 at
+// columns 128 i + 4 l (i < V = C/16) -- the same element-to-lane map and the same summation order as
+// ln_fwd_fast_kernel<., 32, V>, so the statistics are bit-identical to gather + LayerNorm -- and reads each of them
+// from its source token.  The backward writes dx straight to the source tokens (every real token of the stage grid
+// belongs to exactly one merged row) and accumulates dgamma / dbeta in registers over a persistent row loop.
+struct MergeGeom {
+  int pD, pH, pW;     // padded stage grid the source rows live on
+  int rD, rH, rW;     // real grid (crop): sources beyond it read as zero
+  int oD, oH, oW;     // merged grid
+};
+// source row of segment q of merged row `row`, or -1 when it lies beyond the real grid
+__device__ __forceinline__ long long merge_src_row(const MergeGeom& g, long long row, int q) {
+  unsigned t = static_cast<unsigned>(row);            // rows < 2^31 (checked by the host): 32-bit divisions
+  unsigned u = t / static_cast<unsigned>(g.oW);
+  const int w = static_cast<int>(t - u * g.oW); t = u;
+  u = t / static_cast<unsigned>(g.oH);
+  const int h = static_cast<int>(t - u * g.oH); t = u;
+  u = t / static_cast<unsigned>(g.oD);
+  const int d = static_cast<int>(t - u * g.oD);
+  const long long b = u;
+  const int sd = 2 * d + ((0xB2 >> q) & 1), sh = 2 * h + ((0xD4 >> q) & 1), sw = 2 * w + ((0xE8 >> q) & 1);
+  if (sd >= g.rD || sh >= g.rH || sw >= g.rW) return -1;
+  return ((b * g.pD + sd) * g.pH + sh) * g.pW + sw;
+}
+
+template <int C>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_merge_fwd_kernel(const float* __restrict__ x, MergeGeom geo,
+                                                                     const float* __restrict__ gamma,
+                                                                     const float* __restrict__ beta,
+                                                                     bf16* __restrict__ y, float* __restrict__ mean_out,
+                                                                     float* __restrict__ rstd_out, long long rows,
+                                                                     float eps) {
+  pdl_trigger();
+  constexpr int C8 = 8 * C, V = C8 / 128;
+  static_assert(C % 32 == 0 && C8 % 128 == 0, "a float4 never straddles two segments and lanes cover the row evenly");
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  // the eight source rows of this merged row: lane q < 8 computes its own, then broadcasts
+  long long mine = lane < 8 ? merge_src_row(geo, row, lane) : -1;
+  float4 v[V];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int j = 128 * i + 4 * lane, q = j / C, cc = j - q * C;
+    const long long src = __shfl_sync(0xffffffffu, mine, q);
+    v[i] = src >= 0 ? *reinterpret_cast<const float4*>(x + src * C + cc) : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mu = warp_sum(s) * (1.0f / C8);
+  float qs = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
+    qs += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(qs) * (1.0f / C8) + eps);
+  bf16* yr = y + row * C8;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int j = 128 * i + 4 * lane;
+    const float4 g = *reinterpret_cast<const float4*>(gamma + j);
+    const float4 b = *reinterpret_cast<const float4*>(beta + j);
+    uint2 u;
+    u.x = pack_bf16((v[i].x - mu) * rstd * g.x + b.x, (v[i].y - mu) * rstd * g.y + b.y);
+    u.y = pack_bf16((v[i].z - mu) * rstd * g.z + b.z, (v[i].w - mu) * rstd * g.w + b.w);
+    *reinterpret_cast<uint2*>(yr + j) = u;
+  }
+  if (lane == 0) {
+    mean_out[row] = mu;
+    rstd_out[row] = rstd;
+  }
+}
+
+// CH = float4 per lane handled at a time.  V == CH: the row stays in registers between the statistics and the dx
+// pass; V > CH: the second pass re-reads x / dy (the warp's own 4.5 KB per row: L1 hits) so that the registers go
+// to the dgamma / dbeta accumulators of ALL the lane's columns.  The kernel is latency-bound on its register budget
+// (accumulators + one row): blocks of MB_WARPS = 4 warps so that three or four of them share an SM.
+constexpr int MB_WARPS = 4;
+template <int C>
+__global__ void __launch_bounds__(MB_WARPS * 32, (C <= 96 ? 4 : 2)) ln_merge_bwd_kernel(
+    const bf16* __restrict__ dy, const float* __restrict__ x, MergeGeom geo, const float* __restrict__ mean,
+    const float* __restrict__ rstd, const float* __restrict__ gamma, float* __restrict__ dx, long long rows,
+    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_trigger();
+  constexpr int C8 = 8 * C, V = C8 / 128, CH = 6, NCH = V / CH;
+  static_assert(V % CH == 0, "row = whole chunks");
+  __shared__ float red[MB_WARPS][CH * 128 + 4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 ag[V], ab[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long stride = static_cast<long long>(gridDim.x) * MB_WARPS;
+  for (long long row = static_cast<long long>(blockIdx.x) * MB_WARPS + warp; row < rows; row += stride) {
+    const long long mine = lane < 8 ? merge_src_row(geo, row, lane) : -1;
+    const float mu = mean[row], rs = rstd[row];
+    const bf16* dyr = dy + row * C8;
+    float4 xv[CH], d[CH];
+    int off[CH];                  // float4 index of this lane's element in x / dx, or -1 beyond the real grid
+    float s1 = 0.f, s2 = 0.f;
+    auto load = [&](int ch) {
+#pragma unroll
+      for (int k = 0; k < CH; ++k) {
+        const int j = 128 * (ch * CH + k) + 4 * lane, q = j / C, cc = j - q * C;
+        const long long src = __shfl_sync(0xffffffffu, mine, q);
+        off[k] = src >= 0 ? static_cast<int>(src * (C / 4)) + (cc >> 2) : -1;
+      }
+#pragma unroll
+      for (int k = 0; k < CH; ++k) {
+        const int j = 128 * (ch * CH + k) + 4 * lane;
+        xv[k] = off[k] >= 0 ? reinterpret_cast<const float4*>(x)[off[k]] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint2 u = *reinterpret_cast<const uint2*>(dyr + j);
+        const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+        d[k] = make_float4(a.x, a.y, b.x, b.y);
+      }
+#pragma unroll
+      for (int k = 0; k < CH; ++k) {
+        xv[k].x = (xv[k].x - mu) * rs; xv[k].y = (xv[k].y - mu) * rs;      // xhat
+        xv[k].z = (xv[k].z - mu) * rs; xv[k].w = (xv[k].w - mu) * rs;
+      }
+    };
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      load(ch);
+#pragma unroll
+      for (int k = 0; k < CH; ++k) {
+        const int i = ch * CH + k;
+        ab[i].x += d[k].x; ab[i].y += d[k].y; ab[i].z += d[k].z; ab[i].w += d[k].w;
+        ag[i].x = fmaf(d[k].x, xv[k].x, ag[i].x); ag[i].y = fmaf(d[k].y, xv[k].y, ag[i].y);
+        ag[i].z = fmaf(d[k].z, xv[k].z, ag[i].z); ag[i].w = fmaf(d[k].w, xv[k].w, ag[i].w);
+        const float4 g = *reinterpret_cast<const float4*>(gamma + 128 * i + 4 * lane);
+        d[k].x *= g.x; d[k].y *= g.y; d[k].z *= g.z; d[k].w *= g.w;
+        s1 += (d[k].x + d[k].y) + (d[k].z + d[k].w);
+        s2 += (d[k].x * xv[k].x + d[k].y * xv[k].y) + (d[k].z * xv[k].z + d[k].w * xv[k].w);
+      }
+    }
+    s1 = warp_sum(s1) * (1.0f / C8);
+    s2 = warp_sum(s2) * (1.0f / C8);    // mean(dy*g*xhat)
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      if (NCH > 1) {
+        load(ch);
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+          const float4 g = *reinterpret_cast<const float4*>(gamma + 128 * (ch * CH + k) + 4 * lane);
+          d[k].x *= g.x; d[k].y *= g.y; d[k].z *= g.z; d[k].w *= g.w;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < CH; ++k) {
+        if (off[k] >= 0)
+          reinterpret_cast<float4*>(dx)[off[k]] =
+              make_float4(rs * (d[k].x - s1 - xv[k].x * s2), rs * (d[k].y - s1 - xv[k].y * s2),
+                          rs * (d[k].z - s1 - xv[k].z * s2), rs * (d[k].w - s1 - xv[k].w * s2));
+      }
+    }
+  }
+  // fold the warps of the block chunk by chunk (smem), then one atomic per column and block
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+#pragma unroll
+      for (int k = 0; k < CH; ++k)
+        *reinterpret_cast<float4*>(&red[warp][128 * k + 4 * lane]) = which ? ab[ch * CH + k] : ag[ch * CH + k];
+      __syncthreads();
+      for (int col = threadIdx.x; col < CH * 128; col += MB_WARPS * 32) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < MB_WARPS; ++w) t += red[w][col];
+        atomicAdd((which ? dbeta : dgamma) + ch * CH * 128 + col, t);
+      }
+      __syncthreads();
+    }
+  }
+}
+
 struct LnShape { int lpr, v; };
 __host__ inline LnShape ln_fast_shape(int C) {
   static const int table[][2] = {{8, 2}, {8, 3}, {8, 4}, {16, 3}, {16, 4}, {32, 3}, {32, 4}, {32, 6}};
@@ -513,6 +693,58 @@ extern "C" int vsn_colreduce(const void* dy, long long lddy, int dy_bf16, const 
   else
     colreduce_kernel<float><<<grid, block, 0, s>>>(reinterpret_cast<const float*>(dy), lddy, x, ldx, mean, rstd,
                                                      dgamma, dbeta, rows, C);
+  VSN_LAUNCH_CHECK();
+  return 0;
+}
+
+static bool merge_ln_geom(int pD, int pH, int pW, int rD, int rH, int rW, MergeGeom& g) {
+  g = {pD, pH, pW, rD, rH, rW, (rD + 1) / 2, (rH + 1) / 2, (rW + 1) / 2};
+  return rD <= pD && rH <= pH && rW <= pW && rD > 0 && rH > 0 && rW > 0;
+}
+
+// PatchMerging gather + LayerNorm(8C) in one pass: y[(b,d,h,w), :] = LN(concat of the 2x2x2 neighbours of x) as the
+// bf16 operand of the reduction GEMM; mean / rstd [rows] for the backward.  C = 96 or 192 (the stages whose merged row
+// a warp holds in registers); other widths use vsn_merge_gather + vsn_layernorm_fwd.
+extern "C" int vsn_merge_ln_fwd(const float* x, int pD, int pH, int pW, int rD, int rH, int rW, int B, int C,
+                                const float* gamma, const float* beta, void* y, float* mean, float* rstd, float eps,
+                                void* stream) {
+  MergeGeom g;
+  VSN_CHECK(merge_ln_geom(pD, pH, pW, rD, rH, rW, g), "vsn_merge_ln_fwd: bad grid (%d,%d,%d) / (%d,%d,%d)", pD, pH, pW,
+            rD, rH, rW);
+  VSN_CHECK(C == 96 || C == 192, "vsn_merge_ln_fwd: C must be 96 or 192 (got %d)", C);
+  const long long rows = static_cast<long long>(B) * g.oD * g.oH * g.oW;
+  if (rows == 0) return 0;
+  VSN_CHECK(rows < (1LL << 31), "vsn_merge_ln_fwd: too many merged rows (%lld)", rows);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned grid = static_cast<unsigned>(ceil_div_ll(rows, LN_WARPS));
+  if (C == 96) ln_merge_fwd_kernel<96><<<grid, LN_WARPS * 32, 0, s>>>(x, g, gamma, beta, reinterpret_cast<bf16*>(y), mean, rstd, rows, eps);
+  else ln_merge_fwd_kernel<192><<<grid, LN_WARPS * 32, 0, s>>>(x, g, gamma, beta, reinterpret_cast<bf16*>(y), mean, rstd, rows, eps);
+  VSN_LAUNCH_CHECK();
+  return 0;
+}
+
+// Backward of the above: dx[source token, :] = LayerNorm backward of dy [rows, 8C] (bf16), written to the source tokens
+// on the padded stage grid (tokens outside the real grid are NOT written: the caller zeroes dx when pD,pH,pW differ
+// from rD,rH,rW); dgamma / dbeta [8C] accumulate (+=).
+extern "C" int vsn_merge_ln_bwd(const void* dy, const float* x, int pD, int pH, int pW, int rD, int rH, int rW, int B,
+                                int C, const float* mean, const float* rstd, const float* gamma, float* dx,
+                                float* dgamma, float* dbeta, void* stream) {
+  MergeGeom g;
+  VSN_CHECK(merge_ln_geom(pD, pH, pW, rD, rH, rW, g), "vsn_merge_ln_bwd: bad grid (%d,%d,%d) / (%d,%d,%d)", pD, pH, pW,
+            rD, rH, rW);
+  VSN_CHECK(C == 96 || C == 192, "vsn_merge_ln_bwd: C must be 96 or 192 (got %d)", C);
+  VSN_CHECK(dgamma != nullptr && dbeta != nullptr, "vsn_merge_ln_bwd: dgamma / dbeta are required");
+  const long long rows = static_cast<long long>(B) * g.oD * g.oH * g.oW;
+  if (rows == 0) return 0;
+  VSN_CHECK(rows < (1LL << 31) && static_cast<long long>(B) * pD * pH * pW * (C / 4) < (1LL << 31),
+            "vsn_merge_ln_bwd: grid too large for 32-bit float4 indices (%lld merged rows)", rows);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long need = ceil_div_ll(rows, MB_WARPS);
+  // persistent blocks (each ends with one atomic per column): a few resident waves
+  const long long cap = (rows * 8LL * C < (1LL << 25) ? 4 : 8) * static_cast<long long>(vsn_num_sms());
+  const unsigned grid = static_cast<unsigned>(need < cap ? need : cap);
+  if (C == 96) ln_merge_bwd_kernel<96><<<grid, MB_WARPS * 32, 0, s>>>(reinterpret_cast<const bf16*>(dy), x, g, mean, rstd, gamma, dx, rows, dgamma, dbeta);
+  else ln_merge_bwd_kernel<192><<<grid, MB_WARPS * 32, 0, s>>>(reinterpret_cast<const bf16*>(dy), x, g, mean, rstd, gamma, dx, rows, dgamma, dbeta);
   VSN_LAUNCH_CHECK();
   return 0;
 }

@@ -251,6 +251,45 @@ def merge_scatter(dout: torch.Tensor, pdims, rdims, B: int, C: int) -> torch.Ten
     return dx
 
 
+MERGE_LN_WIDTHS = (96, 192)     # widths whose merged row (8C) a warp holds in registers: gather fused into LayerNorm
+
+
+def merge_ln_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, pdims, rdims, B: int, C: int,
+                 eps: float = 1e-5) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """PatchMerging's gather + LayerNorm(8C) in one pass (models/swin_transformer_3d.py:553-572): returns the bf16
+    operand of the reduction GEMM [rows, 8C] and mean / rstd [rows]."""
+    assert C in MERGE_LN_WIDTHS and x.dtype == F32 and x.is_contiguous()
+    _require_cuda(x, gamma, beta)
+    od = [(r + 1) // 2 for r in rdims]
+    rows = B * od[0] * od[1] * od[2]
+    y = torch.empty((rows, 8 * C), device=x.device, dtype=BF16)
+    mean = torch.empty(rows, device=x.device, dtype=F32)
+    rstd = torch.empty(rows, device=x.device, dtype=F32)
+    if _lib.PROFILE is not None:
+        _lib.TAG = f"B{B} C{C} real{tuple(rdims)} fwd"
+        _lib.WORK = (0, 4 * B * C * rdims[0] * rdims[1] * rdims[2] + 2 * y.numel())
+    _lib.call("vsn_merge_ln_fwd", _p(x), *pdims, *rdims, B, C, _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), eps,
+              _stream())
+    return y, mean, rstd
+
+
+def merge_ln_bwd(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, gamma: torch.Tensor,
+                 dgamma: torch.Tensor, dbeta: torch.Tensor, pdims, rdims, B: int, C: int) -> torch.Tensor:
+    """Backward of merge_ln_fwd: dx on the padded stage grid [B*pD*pH*pW, C]; dgamma / dbeta accumulate."""
+    assert C in MERGE_LN_WIDTHS and dy.dtype == BF16 and dy.is_contiguous() and x.dtype == F32 and x.is_contiguous()
+    _require_cuda(dy, x, mean, rstd, gamma, dgamma, dbeta)
+    n = B * pdims[0] * pdims[1] * pdims[2]
+    # every token of the real grid belongs to exactly one merged row: only a larger padded grid needs the zero fill
+    alloc = torch.empty if tuple(pdims) == tuple(rdims) else torch.zeros
+    dx = alloc((n, C), device=dy.device, dtype=F32)
+    if _lib.PROFILE is not None:
+        _lib.TAG = f"B{B} C{C} real{tuple(rdims)} bwd"
+        _lib.WORK = (0, 2 * dy.numel() + 8 * B * C * rdims[0] * rdims[1] * rdims[2])
+    _lib.call("vsn_merge_ln_bwd", _p(dy), _p(x), *pdims, *rdims, B, C, _p(mean), _p(rstd), _p(gamma), _p(dx),
+              _p(dgamma), _p(dbeta), _stream())
+    return dx
+
+
 def mixup(x: torch.Tensor, lam: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
     """out[b] = lam[b] * x[b] + (1 - lam[b]) * x[perm[b]] on fp16 volumes [B,1,D,H,W] (dataset/dataset.py:276-281)."""
     assert x.dtype == torch.float16 and x.is_contiguous() and lam.dtype == F32 and perm.dtype == torch.int32

@@ -303,17 +303,22 @@ class PatchMergeFn(torch.autograd.Function):
     def forward(ctx, x, nw, nb, red_w, w16, pdims, rdims, B):
         x = _contig_f32(x)
         C = x.shape[1]
-        xg = ops.merge_gather(x, pdims, rdims, B, C)
-        y, mean, rstd = ops.layernorm_fwd(xg, nw, nb)
+        fused = C in ops.MERGE_LN_WIDTHS          # gather fused into the LayerNorm: the merged fp32 row never exists
+        if fused:
+            y, mean, rstd = ops.merge_ln_fwd(x, nw, nb, pdims, rdims, B, C)
+            xg = x
+        else:
+            xg = ops.merge_gather(x, pdims, rdims, B, C)
+            y, mean, rstd = ops.layernorm_fwd(xg, nw, nb)
         out = ops.linear_fwd(y, w16, None, out_dtype=F32)
-        ctx.meta = (pdims, rdims, B, C, red_w.shape, w16)
+        ctx.meta = (pdims, rdims, B, C, red_w.shape, w16, fused)
         ctx.sink = GradSink.destinations(nw, nb, red_w)
         ctx.save_for_backward(xg, mean, rstd, y, nw)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        pdims, rdims, B, C, wshape, w16 = ctx.meta
+        pdims, rdims, B, C, wshape, w16, fused = ctx.meta
         xg, mean, rstd, y, nw = ctx.saved_tensors
         dev = g.device
         gb = ops.cast_rows_bf16(_contig_f32(g))
@@ -323,8 +328,11 @@ class PatchMergeFn(torch.autograd.Function):
             d_nw, d_nb, d_w = zeros_like_shapes([(8 * C,), (8 * C,), tuple(wshape)], dev)
         ops.linear_wgrad(gb, y, d_w)
         dy = ops.linear_dgrad(gb, w16)
-        dxg, _ = ops.layernorm_bwd(dy, xg, mean, rstd, nw, dgamma=d_nw, dbeta=d_nb)
-        dx = ops.merge_scatter(dxg, pdims, rdims, B, C)
+        if fused:
+            dx = ops.merge_ln_bwd(dy, xg, mean, rstd, nw, d_nw, d_nb, pdims, rdims, B, C)
+        else:
+            dxg, _ = ops.layernorm_bwd(dy, xg, mean, rstd, nw, dgamma=d_nw, dbeta=d_nb)
+            dx = ops.merge_scatter(dxg, pdims, rdims, B, C)
         if ctx.sink is not None:
             GradSink.done(ctx.sink)
             return (dx,) + (None,) * 7
