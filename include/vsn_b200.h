@@ -105,12 +105,13 @@ int vsn_merge_gather(float* x, int pD, int pH, int pW, int rD, int rH, int rW, f
  * norm(8C)): y [B*oD*oH*oW, 8C] bf16 = LN(concat of the 2x2x2 neighbours of x), the operand of the reduction GEMM;
  * mean / rstd per merged row.  The merged fp32 row never exists in HBM.  C = 96 or 192 (other widths: vsn_merge_gather +
  * vsn_layernorm_fwd).  The backward writes dx [B*pD*pH*pW, C] at the source tokens inside the real grid only (zero dx
- * first when the padded grid is larger) and accumulates dgamma / dbeta [8C]. */
+ * first when the padded grid is larger) and accumulates dgamma / dbeta [8C]; dx_bf16 (optional) = dx * row_scale[b]
+ * in the 16-bit operand type, for the block backward that consumes it next. */
 int vsn_merge_ln_fwd(const float* x, int pD, int pH, int pW, int rD, int rH, int rW, int B, int C, const float* gamma,
                      const float* beta, void* y, float* mean, float* rstd, float eps, void* stream);
 int vsn_merge_ln_bwd(const void* dy, const float* x, int pD, int pH, int pW, int rD, int rH, int rW, int B, int C,
                      const float* mean, const float* rstd, const float* gamma, float* dx, float* dgamma, float* dbeta,
-                     void* stream);
+                     void* dx_bf16, const float* row_scale, void* stream);
 /* MixUp of fp16 volumes on the device (dataset/dataset.py:230-286, `sample1*alpha + sample2*(1-alpha)`):
  * out[b] = fp16(fp16(lam[b]*x[b]) + (1-lam[b])*x[perm[b]]) -- the reference's in-place fp16 mul_ then add_;
  * lam [B] fp32 (1 = sample left alone), perm [B] int32; not in place. */

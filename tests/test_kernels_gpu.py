@@ -380,8 +380,11 @@ def test_merge_gather_fused_into_layernorm(C, real, padded):
     dxg, _ = ops.layernorm_bwd(dy, xg, mean_ref, rstd_ref, gamma, dgamma=dg_ref, dbeta=db_ref)
     dx_ref = ops.merge_scatter(dxg, padded, real, B, C)
     dg, db = torch.ones(8 * C, device="cuda"), torch.ones(8 * C, device="cuda")        # accumulate (+=)
-    dx = ops.merge_ln_bwd(dy, xp, mean, rstd, gamma, dg, db, padded, real, B, C)
+    scale = torch.tensor([0.0, 1.0 / 0.7], device="cuda")                              # per-sample DropPath factors
+    dx, dxb = ops.merge_ln_bwd(dy, xp, mean, rstd, gamma, dg, db, padded, real, B, C, want_bf16=True, row_scale=scale)
     assert rel_err(dx, dx_ref) < 1e-6
+    want_b = (dx.reshape(B, -1) * scale[:, None]).reshape(dx.shape).to(dxb.dtype)
+    assert torch.equal(dxb, want_b)
     pad_mask = torch.ones(B, *padded, 1, device="cuda", dtype=torch.bool)
     pad_mask[:, :real[0], :real[1], :real[2]] = False
     assert float((dx.reshape(B, *padded, C) * pad_mask).abs().max()) == 0.0

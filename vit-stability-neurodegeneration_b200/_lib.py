@@ -43,7 +43,7 @@ SIGNATURES = {
     "vsn_grid_copy": [_p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p],
     "vsn_merge_gather": [_p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _p],
     "vsn_merge_ln_fwd": [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _f, _p],
-    "vsn_merge_ln_bwd": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
+    "vsn_merge_ln_bwd": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "vsn_mixup_f16": [_p, _p, _p, _p, _i, _ll, _p],
     "vsn_volume_stats_f16": [_p, _p, _p, _i, _ll, _p, _p, _p],
     "vsn_mixup_zscore_f16": [_p, _p, _p, _p, _p, _i, _ll, _p],

@@ -449,7 +449,8 @@ template <int C>
 __global__ void __launch_bounds__(MB_WARPS * 32, (C <= 96 ? 4 : 2)) ln_merge_bwd_kernel(
     const bf16* __restrict__ dy, const float* __restrict__ x, MergeGeom geo, const float* __restrict__ mean,
     const float* __restrict__ rstd, const float* __restrict__ gamma, float* __restrict__ dx, long long rows,
-    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    float* __restrict__ dgamma, float* __restrict__ dbeta, bf16* __restrict__ dx_bf16,
+    const float* __restrict__ row_scale) {
   pdl_trigger();
   constexpr int C8 = 8 * C, V = C8 / 128, CH = 6, NCH = V / CH;
   static_assert(V % CH == 0, "row = whole chunks");
@@ -462,6 +463,9 @@ __global__ void __launch_bounds__(MB_WARPS * 32, (C <= 96 ? 4 : 2)) ln_merge_bwd
   for (long long row = static_cast<long long>(blockIdx.x) * MB_WARPS + warp; row < rows; row += stride) {
     const long long mine = lane < 8 ? merge_src_row(geo, row, lane) : -1;
     const float mu = mean[row], rs = rstd[row];
+    float bscale = 1.f;
+    if (dx_bf16 != nullptr && row_scale != nullptr)
+      bscale = row_scale[static_cast<unsigned>(row) / static_cast<unsigned>(geo.oD * geo.oH * geo.oW)];
     const bf16* dyr = dy + row * C8;
     float4 xv[CH], d[CH];
     int off[CH];                  // float4 index of this lane's element in x / dx, or -1 beyond the real grid
@@ -516,10 +520,17 @@ __global__ void __launch_bounds__(MB_WARPS * 32, (C <= 96 ? 4 : 2)) ln_merge_bwd
       }
 #pragma unroll
       for (int k = 0; k < CH; ++k) {
-        if (off[k] >= 0)
-          reinterpret_cast<float4*>(dx)[off[k]] =
-              make_float4(rs * (d[k].x - s1 - xv[k].x * s2), rs * (d[k].y - s1 - xv[k].y * s2),
-                          rs * (d[k].z - s1 - xv[k].z * s2), rs * (d[k].w - s1 - xv[k].w * s2));
+        if (off[k] >= 0) {
+          const float4 o = make_float4(rs * (d[k].x - s1 - xv[k].x * s2), rs * (d[k].y - s1 - xv[k].y * s2),
+                                       rs * (d[k].z - s1 - xv[k].z * s2), rs * (d[k].w - s1 - xv[k].w * s2));
+          reinterpret_cast<float4*>(dx)[off[k]] = o;
+          if (dx_bf16 != nullptr) {       // the copy the previous block's backward starts from (its DropPath factor)
+            uint2 u;
+            u.x = pack_bf16(o.x * bscale, o.y * bscale);
+            u.y = pack_bf16(o.z * bscale, o.w * bscale);
+            reinterpret_cast<uint2*>(dx_bf16)[off[k]] = u;
+          }
+        }
       }
     }
   }
@@ -725,10 +736,11 @@ extern "C" int vsn_merge_ln_fwd(const float* x, int pD, int pH, int pW, int rD, 
 
 // Backward of the above: dx[source token, :] = LayerNorm backward of dy [rows, 8C] (bf16), written to the source tokens
 // on the padded stage grid (tokens outside the real grid are NOT written: the caller zeroes dx when pD,pH,pW differ
-// from rD,rH,rW); dgamma / dbeta [8C] accumulate (+=).
+// from rD,rH,rW); dgamma / dbeta [8C] accumulate (+=).  dx_bf16 (optional, same shape): dx * row_scale[b] as the 16-bit
+// operand the previous block's backward starts from (row_scale = its MLP DropPath factor per sample, or null).
 extern "C" int vsn_merge_ln_bwd(const void* dy, const float* x, int pD, int pH, int pW, int rD, int rH, int rW, int B,
                                 int C, const float* mean, const float* rstd, const float* gamma, float* dx,
-                                float* dgamma, float* dbeta, void* stream) {
+                                float* dgamma, float* dbeta, void* dx_bf16, const float* row_scale, void* stream) {
   MergeGeom g;
   VSN_CHECK(merge_ln_geom(pD, pH, pW, rD, rH, rW, g), "vsn_merge_ln_bwd: bad grid (%d,%d,%d) / (%d,%d,%d)", pD, pH, pW,
             rD, rH, rW);
@@ -743,8 +755,8 @@ extern "C" int vsn_merge_ln_bwd(const void* dy, const float* x, int pD, int pH, 
   // persistent blocks (each ends with one atomic per column): a few resident waves
   const long long cap = (rows * 8LL * C < (1LL << 25) ? 4 : 8) * static_cast<long long>(vsn_num_sms());
   const unsigned grid = static_cast<unsigned>(need < cap ? need : cap);
-  if (C == 96) ln_merge_bwd_kernel<96><<<grid, MB_WARPS * 32, 0, s>>>(reinterpret_cast<const bf16*>(dy), x, g, mean, rstd, gamma, dx, rows, dgamma, dbeta);
-  else ln_merge_bwd_kernel<192><<<grid, MB_WARPS * 32, 0, s>>>(reinterpret_cast<const bf16*>(dy), x, g, mean, rstd, gamma, dx, rows, dgamma, dbeta);
+  if (C == 96) ln_merge_bwd_kernel<96><<<grid, MB_WARPS * 32, 0, s>>>(reinterpret_cast<const bf16*>(dy), x, g, mean, rstd, gamma, dx, rows, dgamma, dbeta, reinterpret_cast<bf16*>(dx_bf16), row_scale);
+  else ln_merge_bwd_kernel<192><<<grid, MB_WARPS * 32, 0, s>>>(reinterpret_cast<const bf16*>(dy), x, g, mean, rstd, gamma, dx, rows, dgamma, dbeta, reinterpret_cast<bf16*>(dx_bf16), row_scale);
   VSN_LAUNCH_CHECK();
   return 0;
 }

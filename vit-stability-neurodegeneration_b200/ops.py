@@ -274,20 +274,23 @@ def merge_ln_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, pdims
 
 
 def merge_ln_bwd(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, gamma: torch.Tensor,
-                 dgamma: torch.Tensor, dbeta: torch.Tensor, pdims, rdims, B: int, C: int) -> torch.Tensor:
-    """Backward of merge_ln_fwd: dx on the padded stage grid [B*pD*pH*pW, C]; dgamma / dbeta accumulate."""
+                 dgamma: torch.Tensor, dbeta: torch.Tensor, pdims, rdims, B: int, C: int, *, want_bf16: bool = False,
+                 row_scale: Optional[torch.Tensor] = None):
+    """Backward of merge_ln_fwd: dx on the padded stage grid [B*pD*pH*pW, C]; dgamma / dbeta accumulate.  Returns
+    (dx, dx_bf16 or None); dx_bf16 = dx * row_scale[sample] for the block backward that consumes dx next."""
     assert C in MERGE_LN_WIDTHS and dy.dtype == BF16 and dy.is_contiguous() and x.dtype == F32 and x.is_contiguous()
     _require_cuda(dy, x, mean, rstd, gamma, dgamma, dbeta)
     n = B * pdims[0] * pdims[1] * pdims[2]
     # every token of the real grid belongs to exactly one merged row: only a larger padded grid needs the zero fill
     alloc = torch.empty if tuple(pdims) == tuple(rdims) else torch.zeros
     dx = alloc((n, C), device=dy.device, dtype=F32)
+    dxb = alloc((n, C), device=dy.device, dtype=BF16) if want_bf16 else None
     if _lib.PROFILE is not None:
-        _lib.TAG = f"B{B} C{C} real{tuple(rdims)} bwd"
-        _lib.WORK = (0, 2 * dy.numel() + 8 * B * C * rdims[0] * rdims[1] * rdims[2])
+        _lib.TAG = f"B{B} C{C} real{tuple(rdims)} bwd dxb={int(want_bf16)}"
+        _lib.WORK = (0, 2 * dy.numel() + (8 + (2 if want_bf16 else 0)) * B * C * rdims[0] * rdims[1] * rdims[2])
     _lib.call("vsn_merge_ln_bwd", _p(dy), _p(x), *pdims, *rdims, B, C, _p(mean), _p(rstd), _p(gamma), _p(dx),
-              _p(dgamma), _p(dbeta), _stream())
-    return dx
+              _p(dgamma), _p(dbeta), _p(dxb), _p(row_scale) if want_bf16 else None, _stream())
+    return dx, dxb
 
 
 def mixup(x: torch.Tensor, lam: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:

@@ -300,10 +300,15 @@ class PatchMergeFn(torch.autograd.Function):
     (models/swin_transformer_3d.py:508,553-572).  x lives on the padded stage grid."""
 
     @staticmethod
-    def forward(ctx, x, nw, nb, red_w, w16, pdims, rdims, B):
+    def forward(ctx, x, nw, nb, red_w, w16, pdims, rdims, B, prev_cfg=None):
         x = _contig_f32(x)
         C = x.shape[1]
         fused = C in ops.MERGE_LN_WIDTHS          # gather fused into the LayerNorm: the merged fp32 row never exists
+        # backward hand-over to the last block of the stage (see BlockCfg): the fused backward also writes the bf16
+        # copy of dx scaled by that block's MLP DropPath factor, which the block would otherwise cast itself
+        ctx.prev_cfg = prev_cfg if fused else None
+        if ctx.prev_cfg is not None:
+            prev_cfg.take_from_next = True
         if fused:
             y, mean, rstd = ops.merge_ln_fwd(x, nw, nb, pdims, rdims, B, C)
             xg = x
@@ -329,14 +334,19 @@ class PatchMergeFn(torch.autograd.Function):
         ops.linear_wgrad(gb, y, d_w)
         dy = ops.linear_dgrad(gb, w16)
         if fused:
-            dx = ops.merge_ln_bwd(dy, xg, mean, rstd, nw, d_nw, d_nb, pdims, rdims, B, C)
+            pc = ctx.prev_cfg
+            dx, dxb = ops.merge_ln_bwd(dy, xg, mean, rstd, nw, d_nw, d_nb, pdims, rdims, B, C,
+                                       want_bf16=pc is not None, row_scale=pc.scale2 if pc is not None else None)
+            if pc is not None:
+                _SIDE.clear()
+                _SIDE[dx.data_ptr()] = dxb
         else:
             dxg, _ = ops.layernorm_bwd(dy, xg, mean, rstd, nw, dgamma=d_nw, dbeta=d_nb)
             dx = ops.merge_scatter(dxg, pdims, rdims, B, C)
         if ctx.sink is not None:
             GradSink.done(ctx.sink)
-            return (dx,) + (None,) * 7
-        return dx, d_nw, d_nb, d_w, None, None, None, None
+            return (dx,) + (None,) * 8
+        return dx, d_nw, d_nb, d_w, None, None, None, None, None
 
 
 class NormPoolHeadFn(torch.autograd.Function):

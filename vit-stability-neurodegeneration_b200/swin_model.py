@@ -273,7 +273,7 @@ class SwinTransformer3DBackbone(nn.Module):
             if layer.downsample is not None:
                 ds = layer.downsample
                 t = swin.PatchMergeFn.apply(t, W(ds.norm.weight), W(ds.norm.bias), W(ds.reduction.weight),
-                                            self._shadow.view(wi), pdims, real, B)
+                                            self._shadow.view(wi), pdims, real, B, prev_cfg)
                 wi += 1
                 real = tuple((r + 1) // 2 for r in real)
             elif pdims != real:
