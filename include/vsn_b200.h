@@ -93,6 +93,14 @@ int vsn_attn_bwd(const void* qkv, const void* out, const void* dout, const float
  * in_dtype 0 fp32 / 1 fp16 / 2 bf16; rows are bf16 (out_bf16=1) or fp32. */
 int vsn_patch_gather(const void* vol, int in_dtype, void* out, int out_bf16, int B, int D, int H, int W, int pd,
                      int ph, int pw, void* stream);
+/* ViT to_patch_embedding head, Rearrange + LayerNorm(P) in one pass (models/vit_3d.py:364-371): y [B*gd*gh*gw, P]
+ * (16-bit operand of the embedding GEMM) and mean / rstd per patch, read straight from the volume -- the fp32 patch
+ * rows never exist in HBM.  pd*ph <= 1024 threads, pw <= 16.  vsn_patch_ln_param_grad: dgamma / dbeta [P] += of that
+ * LayerNorm from dy [., P] (16-bit), with xhat re-gathered from the volume (its input is data: no dx). */
+int vsn_patch_ln_fwd(const void* vol, int in_dtype, int B, int D, int H, int W, int pd, int ph, int pw,
+                     const float* gamma, const float* beta, void* y, float* mean, float* rstd, float eps, void* stream);
+int vsn_patch_ln_param_grad(const void* dy, const void* vol, int in_dtype, int B, int D, int H, int W, int pd, int ph,
+                            int pw, const float* mean, const float* rstd, float* dgamma, float* dbeta, void* stream);
 /* Copy the overlap of two channels-last fp32 grids, zero-fill the rest: stage pad / crop
  * (models/swin_transformer_3d.py:457-461,508) and their gradients. */
 int vsn_grid_copy(const float* src, int sD, int sH, int sW, float* dst, int dD, int dH, int dW, int B, int C,

@@ -332,6 +332,35 @@ def test_patch_gather_444_fast_path_bit_exact(dtype, shape):
     assert rows.dtype == torch.bfloat16 and torch.equal(rows, ref.to(torch.bfloat16))
 
 
+@pytest.mark.parametrize("dtype,shape,patch", [(torch.float16, (2, 32, 48, 32), (16, 16, 16)),
+                                               (torch.float16, (2, 20, 33, 30), (16, 16, 16)),
+                                               (torch.float32, (3, 8, 9, 8), (4, 8, 4)),
+                                               (torch.bfloat16, (2, 16, 16, 22), (4, 8, 8))])
+def test_patch_gather_fused_into_layernorm(dtype, shape, patch):
+    """vsn_patch_ln_fwd / vsn_patch_ln_param_grad (ViT Rearrange + LayerNorm(P), models/vit_3d.py:364-371) against the
+    composition patch_gather -> layernorm -> column reduction; ragged volumes (zero-padded patches) included."""
+    ops = _ops()
+    B, D, H, W = shape
+    P = patch[0] * patch[1] * patch[2]
+    vol = _rand(B, 1, D, H, W, seed=1).to(dtype)
+    gamma, beta = 1.0 + 0.1 * _rand(P, seed=2), 0.1 * _rand(P, seed=3)
+    rows = ops.patch_gather(vol, patch, out_dtype=torch.float32)
+    y_ref, mean_ref, rstd_ref = ops.layernorm_fwd(rows, gamma, beta)
+    assert ops.patch_ln_supported(patch, vol)
+    y, mean, rstd = ops.patch_ln_fwd(vol, patch, gamma, beta)
+    if P > 1024:      # LayerNorm(P) takes the generic kernel, whose lane map and summation order the fused one follows
+        assert torch.equal(mean, mean_ref) and torch.equal(rstd, rstd_ref) and torch.equal(y, y_ref)
+    else:             # the register-resident LayerNorm kernels sum in another order: fp32 round-off
+        assert rel_err(mean, mean_ref) < 1e-5 and rel_err(rstd, rstd_ref) < 1e-5
+        assert rel_err(y.float(), y_ref.float()) < 1e-3
+    dy = _rand(*y.shape, seed=4).to(y.dtype)
+    dg_ref, db_ref = torch.zeros(P, device="cuda"), torch.zeros(P, device="cuda")
+    ops.ln_param_grad(dy, rows, mean_ref, rstd_ref, dg_ref, db_ref)
+    dg, db = torch.ones(P, device="cuda"), torch.ones(P, device="cuda")               # accumulate (+=)
+    ops.patch_ln_param_grad(dy, vol, patch, mean, rstd, dg, db)
+    assert rel_err(dg - 1.0, dg_ref) < 1e-4 and rel_err(db - 1.0, db_ref) < 1e-4
+
+
 def test_grid_copy_and_merge_gather_bit_exact():
     ops = _ops()
     B, C = 2, 32

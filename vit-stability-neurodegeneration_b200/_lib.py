@@ -40,6 +40,8 @@ SIGNATURES = {
     "vsn_attn_fwd": [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _f, _p],
     "vsn_attn_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _f, _p],
     "vsn_patch_gather": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "vsn_patch_ln_fwd": [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _f, _p],
+    "vsn_patch_ln_param_grad": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p],
     "vsn_grid_copy": [_p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p],
     "vsn_merge_gather": [_p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _p],
     "vsn_merge_ln_fwd": [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _f, _p],

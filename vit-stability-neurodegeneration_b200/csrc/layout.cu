@@ -463,6 +463,187 @@ __global__ void __launch_bounds__(256) tta_views_f16_kernel(const __half* __rest
   }
 }
 
+// ---- ViT to_patch_embedding head: Rearrange + LayerNorm(P) in one pass (models/vit_3d.py:364-371) ---------------
+// The [T, P] fp32 rows of the Rearrange never exist in HBM (at vit-3c: 637 MB written and read twice per step).
+// A block owns the SLAB of one (b, d, h): the pd*ph volume rows of its gw patches, W voxels each.  It stages the slab
+// in shared memory with 16-byte loads -- for fixed i the ph rows are one contiguous run of the volume (4.6 KB at
+// vit-3c), where per-patch reads would be 32-byte pieces at a 288-byte stride, half of every DRAM burst wasted (the
+// first version of this kernel, one block per patch, ran at 1.5 TB/s) -- and then works on the patches out of it.
+constexpr int PLN_MAXW = 16;      // voxels of one patch row (pgrad: held by a thread)
+constexpr int PLN_GROUPS = 32;    // float4 groups per lane in the forward (P <= 4096)
+
+struct PatchGeom { int B, D, H, W, gd, gh, gw, pd, ph, pw, pw_shift, ph_shift, Wp; };   // shifts: log2 or -1; Wp = gw*pw
+
+// slab[row = i*ph + j][x < Wp] <- vol[b, d*pd + i, h*ph + j, x] (zero beyond D, H, W); all threads of the block
+template <typename InT>
+__device__ __forceinline__ void stage_slab(const InT* __restrict__ vol, const PatchGeom& g, unsigned slab_id, InT* slab) {
+  unsigned t = slab_id;
+  const int h = t % g.gh; t /= g.gh;
+  const int d = t % g.gd;
+  const long long b = t / g.gd;
+  constexpr int VE = 16 / sizeof(InT);                 // elements per 16-byte chunk
+  const int rows = g.pd * g.ph;
+  const bool vec = (g.W % VE == 0) && (g.Wp % VE == 0) && ((reinterpret_cast<uintptr_t>(vol) & 15) == 0);
+  if (vec) {
+    // batches of eight chunks per thread: all eight loads are in flight before the first shared-memory store needs one
+    // (one load - one store per trip made every trip a full memory round trip: 16 of them per thread at vit-3c)
+    const int cpr = g.Wp / VE, total = rows * cpr;
+    constexpr int NB = 8;
+    for (int base = threadIdx.x; base < total; base += NB * blockDim.x) {
+      uint4 u[NB];
+      int dst[NB];
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+        const int idx = base + k * blockDim.x;
+        u[k] = make_uint4(0, 0, 0, 0);
+        dst[k] = -1;
+        if (idx < total) {
+          const int row = idx / cpr, c = idx - row * cpr;
+          const int pi = g.ph_shift >= 0 ? row >> g.ph_shift : row / g.ph, pj = row - pi * g.ph;
+          const int zd = d * g.pd + pi, zh = h * g.ph + pj;
+          dst[k] = row * g.Wp + c * VE;
+          if (zd < g.D && zh < g.H && (c + 1) * VE <= g.W)
+            u[k] = *reinterpret_cast<const uint4*>(vol + ((b * g.D + zd) * g.H + zh) * g.W + c * VE);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < NB; ++k)
+        if (dst[k] >= 0) *reinterpret_cast<uint4*>(slab + dst[k]) = u[k];
+    }
+  } else {
+    const int total = rows * g.Wp;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+      const int row = idx / g.Wp, x = idx - row * g.Wp;
+      const int pi = row / g.ph, pj = row - pi * g.ph;
+      const int zd = d * g.pd + pi, zh = h * g.ph + pj;
+      InT v;
+      memset(&v, 0, sizeof(InT));
+      if (zd < g.D && zh < g.H && x < g.W) v = vol[((b * g.D + zd) * g.H + zh) * g.W + x];
+      slab[idx] = v;
+    }
+  }
+}
+
+// Forward: block = one slab, warp w = patch w of the slab.  Lane l walks the float4 groups j = l + 32 i of the patch's
+// P values exactly as the generic LayerNorm kernel walks a row (same partial sums, same butterfly, same expressions),
+// so statistics and normalised values are bit-identical to patch_gather + vsn_layernorm_fwd; group j is the 4 voxels
+// k0 = 4 j % pw of patch row 4 j / pw.  pw % 4 == 0, P % 128 == 0.
+template <typename InT>
+__global__ void patch_ln_fwd_kernel(const InT* __restrict__ vol, PatchGeom g, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, bf16* __restrict__ y, float* __restrict__ mean_out,
+                                    float* __restrict__ rstd_out, float eps) {
+  pdl_trigger();
+  extern __shared__ __align__(16) uint8_t pln_smem[];
+  InT* slab = reinterpret_cast<InT*>(pln_smem);
+  stage_slab<InT>(vol, g, blockIdx.x, slab);
+  __syncthreads();
+  const int P = g.pd * g.ph * g.pw, nvec = P >> 2;
+  const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int w = threadIdx.x >> 5; w < g.gw; w += nwarps) {
+    const unsigned token = blockIdx.x * g.gw + w;
+    const InT* base = slab + w * g.pw;
+    auto group = [&](int j, float* f) {
+      const int e = 4 * j, row = g.pw_shift >= 0 ? e >> g.pw_shift : e / g.pw, k0 = e - row * g.pw;
+      load4<InT>(base + row * g.Wp + k0, f);
+    };
+    float s = 0.f;
+    for (int j = lane; j < nvec; j += 32) {
+      float f[4];
+      group(j, f);
+      s += (f[0] + f[1]) + (f[2] + f[3]);
+    }
+    const float mu = warp_sum(s) / P;
+    float q = 0.f;
+    for (int j = lane; j < nvec; j += 32) {
+      float f[4];
+      group(j, f);
+      const float a = f[0] - mu, bb = f[1] - mu, c = f[2] - mu, dd = f[3] - mu;
+      q += (a * a + bb * bb) + (c * c + dd * dd);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / P + eps);
+    bf16* yr = y + static_cast<long long>(token) * P;
+    for (int j = lane; j < nvec; j += 32) {
+      float f[4];
+      group(j, f);
+      const float4 ga = *reinterpret_cast<const float4*>(gamma + 4 * j);
+      const float4 be = *reinterpret_cast<const float4*>(beta + 4 * j);
+      const float o0 = (f[0] - mu) * rstd * ga.x + be.x, o1 = (f[1] - mu) * rstd * ga.y + be.y;
+      const float o2 = (f[2] - mu) * rstd * ga.z + be.z, o3 = (f[3] - mu) * rstd * ga.w + be.w;
+      uint2 u;
+      u.x = pack_bf16(o0, o1);
+      u.y = pack_bf16(o2, o3);
+      *reinterpret_cast<uint2*>(yr + 4 * j) = u;
+    }
+    if (lane == 0) {
+      mean_out[token] = mu;
+      rstd_out[token] = rstd;
+    }
+  }
+}
+
+// dgamma[c] += sum_t dy[t,c] * xhat[t,c], dbeta[c] += sum_t dy[t,c] with xhat re-gathered from the volume (the input
+// of this LayerNorm is data: there is no dx).  Persistent blocks over slabs, thread (i, j) owns the pw columns of
+// patch row (i, j): its partial sums stay in registers over all patches, one atomic per column and block at the end.
+template <typename InT>
+__global__ void patch_ln_pgrad_kernel(const bf16* __restrict__ dy, const InT* __restrict__ vol, PatchGeom g,
+                                      const float* __restrict__ mean, const float* __restrict__ rstd,
+                                      float* __restrict__ dgamma, float* __restrict__ dbeta, unsigned slabs) {
+  pdl_trigger();
+  extern __shared__ __align__(16) uint8_t pln_smem[];
+  InT* slab = reinterpret_cast<InT*>(pln_smem);
+  const int P = g.pd * g.ph * g.pw;
+  const int c0 = threadIdx.x * g.pw;                    // blockDim.x == pd * ph: thread = patch row
+  float ag[PLN_MAXW], ab[PLN_MAXW];
+#pragma unroll
+  for (int k = 0; k < PLN_MAXW; ++k) ag[k] = ab[k] = 0.f;
+  for (unsigned sid = blockIdx.x; sid < slabs; sid += gridDim.x) {
+    __syncthreads();                                    // the previous slab is no longer read
+    stage_slab<InT>(vol, g, sid, slab);
+    __syncthreads();
+    const InT* myrow = slab + threadIdx.x * g.Wp;
+    constexpr int TB = 3;                               // patches per trip: their dy loads are issued together
+    for (int w0 = 0; w0 < g.gw; w0 += TB) {
+      uint2 raw[TB][PLN_MAXW / 4];
+      float mu[TB], rs[TB];
+#pragma unroll
+      for (int u = 0; u < TB; ++u) {
+        const bool live = w0 + u < g.gw;
+        const unsigned token = sid * g.gw + (live ? w0 + u : w0);
+        const bf16* dyr = dy + static_cast<long long>(token) * P + c0;
+        mu[u] = mean[token];
+        rs[u] = live ? rstd[token] : 0.f;
+#pragma unroll
+        for (int k4 = 0; k4 < PLN_MAXW / 4; ++k4)
+          raw[u][k4] = (live && 4 * k4 < g.pw) ? *reinterpret_cast<const uint2*>(dyr + 4 * k4) : make_uint2(0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < TB; ++u) {
+        const int w = w0 + u < g.gw ? w0 + u : w0;
+#pragma unroll
+        for (int k4 = 0; k4 < PLN_MAXW / 4; ++k4) {
+          if (4 * k4 < g.pw) {
+            float v[4];
+            load4<InT>(myrow + w * g.pw + 4 * k4, v);
+            const float2 d01 = unpack_bf16(raw[u][k4].x), d23 = unpack_bf16(raw[u][k4].y);
+            const float dv[4] = {d01.x, d01.y, d23.x, d23.y};     // a dead slot holds zeros: adds nothing
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              ab[4 * k4 + k] += dv[k];
+              ag[4 * k4 + k] = fmaf(dv[k], (v[k] - mu[u]) * rs[u], ag[4 * k4 + k]);
+            }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < PLN_MAXW; ++k)
+    if (k < g.pw) {
+      atomicAdd(dgamma + c0 + k, ag[k]);
+      atomicAdd(dbeta + c0 + k, ab[k]);
+    }
+}
+
 }  // namespace
 
 // in_dtype: 0 fp32, 1 fp16, 2 bf16.  out_bf16: 1 -> bf16 rows (GEMM operand), 0 -> fp32 rows (feeds LayerNorm).
@@ -650,6 +831,84 @@ extern "C" int vsn_tta_views_f16(const void* vol, void* out, const float* mats, 
   VSN_CHECK(vol != out, "vsn_tta_views_f16: not in place");
   tta_views_f16_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __half*>(vol), reinterpret_cast<__half*>(out), mats, B, V, D, H, W);
+  VSN_LAUNCH_CHECK();
+  return 0;
+}
+
+static int patch_ln_geom(int B, int D, int H, int W, int pd, int ph, int pw, int elem, PatchGeom& g, size_t& smem) {
+  VSN_CHECK(pd > 0 && ph > 0 && pw > 0 && pd * ph <= 1024 && pw <= PLN_MAXW && pw % 4 == 0 &&
+                (pd * ph * pw) % 128 == 0 && pd * ph * pw <= 128 * PLN_GROUPS,
+            "vsn_patch_ln: patch (%d,%d,%d) needs pd*ph <= 1024, pw a multiple of 4 up to %d, P a multiple of 128 up to %d",
+            pd, ph, pw, PLN_MAXW, 128 * PLN_GROUPS);
+  auto lg = [](int v) { int k = 0; while ((1 << k) < v) ++k; return (1 << k) == v ? k : -1; };
+  const int gw = ceil_div(W, pw);
+  g = {B, D, H, W, ceil_div(D, pd), ceil_div(H, ph), gw, pd, ph, pw, lg(pw), lg(ph), gw * pw};
+  VSN_CHECK(static_cast<long long>(B) * g.gd * g.gh * g.gw < (1LL << 31), "vsn_patch_ln: too many patches");
+  smem = static_cast<size_t>(pd) * ph * g.Wp * elem;
+  VSN_CHECK(smem <= 200 * 1024, "vsn_patch_ln: the slab of one patch row (%zu bytes) does not fit shared memory", smem);
+  return 0;
+}
+
+template <typename K>
+static int pln_smem_attr(K kernel, size_t smem) {
+  if (smem > 48 * 1024) VSN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  return 0;
+}
+
+// ViT patch embedding head (models/vit_3d.py:364-371): y [B*gd*gh*gw, P] = LayerNorm(P)(Rearrange(vol)) as the 16-bit
+// operand of the embedding GEMM, mean / rstd per patch; the patch rows are read straight from the volume.
+extern "C" int vsn_patch_ln_fwd(const void* vol, int in_dtype, int B, int D, int H, int W, int pd, int ph, int pw,
+                                const float* gamma, const float* beta, void* y, float* mean, float* rstd, float eps,
+                                void* stream) {
+  VSN_CHECK(in_dtype >= 0 && in_dtype <= 2, "vsn_patch_ln_fwd: bad in_dtype %d", in_dtype);
+  PatchGeom g;
+  size_t smem;
+  if (int rc = patch_ln_geom(B, D, H, W, pd, ph, pw, in_dtype == 0 ? 4 : 2, g, smem)) return rc;
+  const unsigned slabs = static_cast<unsigned>(B) * g.gd * g.gh;
+  if (slabs == 0) return 0;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  bf16* yo = reinterpret_cast<bf16*>(y);
+  const int threads = 32 * (g.gw < 16 ? g.gw : 16);
+#define VSN_PLN_FWD(T)                                                                                        \
+  {                                                                                                           \
+    if (int rc = pln_smem_attr(patch_ln_fwd_kernel<T>, smem)) return rc;                                      \
+    patch_ln_fwd_kernel<T><<<slabs, threads, smem, s>>>(reinterpret_cast<const T*>(vol), g, gamma, beta, yo, mean, rstd, eps); \
+  }
+  if (in_dtype == 0) VSN_PLN_FWD(float)
+  else if (in_dtype == 1) VSN_PLN_FWD(__half)
+  else VSN_PLN_FWD(__nv_bfloat16)
+#undef VSN_PLN_FWD
+  VSN_LAUNCH_CHECK();
+  return 0;
+}
+
+// Parameter gradients of that LayerNorm: dgamma / dbeta [P] += over patches, xhat re-gathered from the volume.
+extern "C" int vsn_patch_ln_param_grad(const void* dy, const void* vol, int in_dtype, int B, int D, int H, int W, int pd,
+                                       int ph, int pw, const float* mean, const float* rstd, float* dgamma, float* dbeta,
+                                       void* stream) {
+  VSN_CHECK(in_dtype >= 0 && in_dtype <= 2, "vsn_patch_ln_param_grad: bad in_dtype %d", in_dtype);
+  PatchGeom g;
+  size_t smem;
+  if (int rc = patch_ln_geom(B, D, H, W, pd, ph, pw, in_dtype == 0 ? 4 : 2, g, smem)) return rc;
+  const unsigned slabs = static_cast<unsigned>(B) * g.gd * g.gh;
+  if (slabs == 0) return 0;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const bf16* dyp = reinterpret_cast<const bf16*>(dy);
+  unsigned grid = 0;
+  // persistent blocks: exactly as many as are resident at once (shared memory decides: two or three per SM)
+#define VSN_PLN_PG(T)                                                                                         \
+  {                                                                                                           \
+    if (int rc = pln_smem_attr(patch_ln_pgrad_kernel<T>, smem)) return rc;                                    \
+    int per_sm = 0;                                                                                           \
+    VSN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, patch_ln_pgrad_kernel<T>, pd * ph, smem)); \
+    const unsigned cap = static_cast<unsigned>(per_sm > 0 ? per_sm : 1) * static_cast<unsigned>(vsn_num_sms()); \
+    grid = slabs < cap ? slabs : cap;                                                                         \
+    patch_ln_pgrad_kernel<T><<<grid, pd * ph, smem, s>>>(dyp, reinterpret_cast<const T*>(vol), g, mean, rstd, dgamma, dbeta, slabs); \
+  }
+  if (in_dtype == 0) VSN_PLN_PG(float)
+  else if (in_dtype == 1) VSN_PLN_PG(__half)
+  else VSN_PLN_PG(__nv_bfloat16)
+#undef VSN_PLN_PG
   VSN_LAUNCH_CHECK();
   return 0;
 }

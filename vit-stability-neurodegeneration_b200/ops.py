@@ -222,6 +222,48 @@ def patch_gather(vol: torch.Tensor, patch: Sequence[int], *, out_dtype=BF16) -> 
     return out
 
 
+def patch_ln_supported(patch: Sequence[int], vol: torch.Tensor) -> bool:
+    """Shapes the fused Rearrange + LayerNorm kernels take: a thread per patch row, four-voxel groups, and the slab of
+    one row of patches (pd*ph volume rows, padded W) in shared memory."""
+    P = patch[0] * patch[1] * patch[2]
+    slab = patch[0] * patch[1] * (-(-vol.shape[-1] // patch[2]) * patch[2]) * vol.element_size()
+    return (vol.dtype in _IN_DTYPE and patch[0] * patch[1] <= 1024 and patch[2] <= 16 and patch[2] % 4 == 0
+            and P % 128 == 0 and P <= 4096 and slab <= 200 * 1024)
+
+
+def patch_ln_fwd(vol: torch.Tensor, patch: Sequence[int], gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5):
+    """ViT Rearrange + LayerNorm(P) in one pass (models/vit_3d.py:364-371): (y bf16 [B*T, P], mean, rstd)."""
+    B, c, D, H, W = vol.shape
+    if c != 1:
+        raise NotImplementedError("vsn_b200 patch embedding supports in_channels=1 (the reference's MRI volumes)")
+    _require_cuda(vol, gamma, beta)
+    assert vol.is_contiguous()
+    pd, ph, pw = patch
+    T = -(-D // pd) * -(-H // ph) * -(-W // pw)
+    y = torch.empty((B * T, pd * ph * pw), device=vol.device, dtype=BF16)
+    mean = torch.empty(B * T, device=vol.device, dtype=F32)
+    rstd = torch.empty(B * T, device=vol.device, dtype=F32)
+    if _lib.PROFILE is not None:
+        _lib.TAG = f"B{B} vol{D}x{H}x{W} patch{pd}x{ph}x{pw} in={vol.dtype} fwd"
+        _lib.WORK = (0, vol.numel() * vol.element_size() + 2 * y.numel())
+    _lib.call("vsn_patch_ln_fwd", _p(vol), _IN_DTYPE[vol.dtype], B, D, H, W, pd, ph, pw, _p(gamma), _p(beta), _p(y),
+              _p(mean), _p(rstd), eps, _stream())
+    return y, mean, rstd
+
+
+def patch_ln_param_grad(dy: torch.Tensor, vol: torch.Tensor, patch: Sequence[int], mean, rstd, dgamma, dbeta) -> None:
+    """dgamma / dbeta [P] += of the LayerNorm in patch_ln_fwd; xhat is re-gathered from the volume."""
+    B, _, D, H, W = vol.shape
+    assert dy.dtype == BF16 and dy.is_contiguous() and vol.is_contiguous()
+    _require_cuda(dy, vol, mean, rstd, dgamma, dbeta)
+    pd, ph, pw = patch
+    if _lib.PROFILE is not None:
+        _lib.TAG = f"B{B} vol{D}x{H}x{W} patch{pd}x{ph}x{pw} in={vol.dtype} pgrad"
+        _lib.WORK = (0, vol.numel() * vol.element_size() + 2 * dy.numel())
+    _lib.call("vsn_patch_ln_param_grad", _p(dy), _p(vol), _IN_DTYPE[vol.dtype], B, D, H, W, pd, ph, pw, _p(mean),
+              _p(rstd), _p(dgamma), _p(dbeta), _stream())
+
+
 def grid_copy(src: torch.Tensor, sdims, ddims, B: int, C: int) -> torch.Tensor:
     dst = torch.empty((B * ddims[0] * ddims[1] * ddims[2], C), device=src.device, dtype=F32)
     if _lib.PROFILE is not None:

@@ -17,27 +17,33 @@ class ViTEmbedFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, vol, ln1w, ln1b, lin_w, lin_b, ln2w, ln2b, cls, pos, w16, patch):
         B = vol.shape[0]
-        rows = ops.patch_gather(vol, patch, out_dtype=F32)                 # [B*T, P]
-        T = rows.shape[0] // B
-        y1, m1, r1 = ops.layernorm_fwd(rows, ln1w, ln1b)
+        fused = ops.patch_ln_supported(patch, vol)
+        if fused:            # Rearrange + LayerNorm(P) in one pass over the volume: no [B*T, P] fp32 rows
+            vol = vol.contiguous()
+            y1, m1, r1 = ops.patch_ln_fwd(vol, patch, ln1w, ln1b)
+            rows = vol
+        else:
+            rows = ops.patch_gather(vol, patch, out_dtype=F32)             # [B*T, P]
+            y1, m1, r1 = ops.layernorm_fwd(rows, ln1w, ln1b)
+        T = y1.shape[0] // B
         z = ops.linear_fwd(y1, w16, lin_b, out_dtype=F32)
         e, m2, r2 = ops.layernorm_fwd(z, ln2w, ln2b, out_dtype=F32)
         C = z.shape[1]
         if pos.shape[1] < T + 1:
             raise ValueError(f"pos_embedding has {pos.shape[1]} positions, input needs {T + 1}")
         x = ops.vit_assemble(e, cls.reshape(-1), pos.reshape(pos.shape[1], C), B, T, C)
-        ctx.meta = (B, T, C, w16, lin_w.shape, cls.shape, pos.shape)
+        ctx.meta = (B, T, C, w16, lin_w.shape, cls.shape, pos.shape, tuple(patch) if fused else None)
         ctx.sink = GradSink.destinations(ln1w, ln1b, lin_w, lin_b, ln2w, ln2b, cls, pos)
         ctx.save_for_backward(rows, m1, r1, y1, z, m2, r2, ln1w, ln2w)
         return x
 
     @staticmethod
     def backward(ctx, g):
-        B, T, C, w16, wshape, cls_shape, pos_shape = ctx.meta
+        B, T, C, w16, wshape, cls_shape, pos_shape, fused_patch = ctx.meta
         rows, m1, r1, y1, z, m2, r2, ln1w, ln2w = ctx.saved_tensors
         g = _contig_f32(g)
         dev = g.device
-        P = rows.shape[1]
+        P = y1.shape[1]
         if ctx.sink is not None:
             d_ln1w, d_ln1b, d_lin_w, d_lin_b, d_ln2w, d_ln2b, d_cls, d_pos = ctx.sink
             d_cls, d_pos = d_cls.view(C), d_pos.view(pos_shape[1], C)
@@ -51,7 +57,10 @@ class ViTEmbedFn(torch.autograd.Function):
         _, dzb = ops.layernorm_bwd(demb, z, m2, r2, ln2w, want_dx=False, want_bf16=True)
         ops.linear_wgrad(dzb, y1, d_lin_w, dbias=d_lin_b)
         dy1 = ops.linear_dgrad(dzb, w16)
-        ops.ln_param_grad(dy1, rows, m1, r1, d_ln1w, d_ln1b)
+        if fused_patch is not None:
+            ops.patch_ln_param_grad(dy1, rows, fused_patch, m1, r1, d_ln1w, d_ln1b)
+        else:
+            ops.ln_param_grad(dy1, rows, m1, r1, d_ln1w, d_ln1b)
         if ctx.sink is not None:
             GradSink.done(ctx.sink)
             return (None,) * 11

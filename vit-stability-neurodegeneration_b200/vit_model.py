@@ -152,6 +152,7 @@ class ViT(nn.Module):
         N = t.shape[0] // B
         wi = 1
         forced = DropPath.forced_masks
+        prev_cfg = None
         for layer in self.transformer.layers:
             attn, ff, dp = layer[0], layer[1], layer[4]
             p = dp.drop_prob if isinstance(dp, DropPath) else 0.0
@@ -159,6 +160,11 @@ class ViT(nn.Module):
                                 w16=tuple(self._shadow.view(wi + j) for j in range(4)),
                                 scale1=swin.droppath_scale(p, B, t.device, self.training, forced),
                                 scale2=swin.droppath_scale(p, B, t.device, self.training, forced))
+            if prev_cfg is not None:
+                # backward hand-over of the bf16 input gradient from this block to the previous one (swin.BlockCfg)
+                cfg.emit_for_prev, cfg.prev_scale2 = True, prev_cfg.scale2
+                prev_cfg.take_from_next = True
+            prev_cfg = cfg
             wi += 4
             t = swin.SwinBlockFn.apply(t, W(attn.norm.weight), W(attn.norm.bias), W(attn.to_qkv.weight), None, None,
                                        W(attn.to_out[0].weight), W(attn.to_out[0].bias), W(ff.net[0].weight),
