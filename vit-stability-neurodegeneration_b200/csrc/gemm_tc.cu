@@ -49,16 +49,23 @@ struct GemmArgs {
 };
 
 // TWO = CTA pair: a CTA holds its 128 rows of A and half of the B tile, so the same smem buys a deeper ring
-template <int BN, bool TWO = false>
+// AUX = number of [128 x BN] tiles of the epilogue's second operand staged in shared memory by TMA (MODE 5: the
+// saved pre-activation of the GELU' epilogue, double-buffered); they come out of the operand ring's budget.
+template <int BN, bool TWO = false, int AUX = 0>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;                       // whole B tile
   static constexpr int B_CTA_BYTES = TWO ? B_BYTES / 2 : B_BYTES;    // what one CTA stores
   static constexpr int STAGE_BYTES = A_BYTES + B_CTA_BYTES;
-  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
+  static constexpr int AUX_TILE_BYTES = BM * BN * 2;
+  static constexpr int AUX_BYTES = AUX * AUX_TILE_BYTES;
+  static constexpr int RING_BUDGET = 192 * 1024 - AUX_BYTES;
+  static constexpr int STAGES = RING_BUDGET / STAGE_BYTES > 8 ? 8 : RING_BUDGET / STAGE_BYTES;
+  static constexpr int MISC = STAGES * STAGE_BYTES + AUX_BYTES;     // barriers, bias slice and ones tile start here
   static constexpr int RS_COL = 2 * BN;              // two 16-column row-sum accumulators after the two tiles
   static constexpr int TMEM_COLS = 2 * BN + 32 <= 128 ? 128 : 2 * BN + 32 <= 256 ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias*/ +
+  static constexpr int SMEM_BYTES = MISC + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias*/ +
                                     2048 /*ones tile*/;
+  static_assert(AUX == 0 || (STAGES >= 2 && BN % 64 == 0), "staged aux tiles: 64-column boxes, at least two ring stages");
   static_assert(STAGE_BYTES % 1024 == 0, "stage bases must keep the 1024-byte alignment of the 128B swizzle");
 };
 
@@ -123,9 +130,14 @@ struct TileIter {
 //   2 = GELU' from the saved pre-activation, bf16 output, 256-bit accesses, full tiles (the fc2 dgrad)
 //   3 = bias + residual + row scale, fp32 output, 256-bit accesses, full tiles (proj / fc2 forward)
 //   4 = optional bias, bf16 output, 256-bit stores, full tiles (qkv forward, plain dgrads)
-template <int MODE>
+//   5 = 2 with the saved pre-activation tile staged in shared memory by TMA (`aux_row` = this thread's row of the
+//       128B-swizzled [128][64] sub-tile the chunk lies in, `aux_c16` = the chunk's first 16-byte column): the epilogue
+//       warps no longer wait for a dependent global load per chunk (the load and the GELU' arithmetic were additive:
+//       0.080 ms stores only, +0.098 the load, +0.083 the arithmetic, 0.239 together at M435456 N384 K96)
+template <int MODE_>
 __device__ __forceinline__ void epilogue_chunk(const GemmArgs& pa, int row, int n, float rs, const uint32_t* v,
-                                               const float* bias_s) {
+                                               const float* bias_s, const uint8_t* aux_row = nullptr, int aux_c16 = 0) {
+  constexpr int MODE = MODE_ == 5 ? 2 : MODE_;
   struct View {       // the fields the epilogue reads, constants where the mode fixes them
     const GemmArgs& a;
     __device__ __forceinline__ int act() const { return MODE == 1 ? 1 : MODE == 2 ? 2 : MODE >= 3 ? 0 : a.act; }
@@ -182,7 +194,16 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& pa, int row, int 
     const bf16* ap = p.aux + static_cast<long long>(row) * p.ldaux + n;
     if (nvalid == 32) {
       uint32_t w[16];
-      if (m.wide()) {
+      if constexpr (MODE_ == 5) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 u = *reinterpret_cast<const uint4*>(aux_row + (((aux_c16 + j) ^ (row & 7)) << 4));
+          w[4 * j] = u.x; w[4 * j + 1] = u.y; w[4 * j + 2] = u.z; w[4 * j + 3] = u.w;
+        }
+      } else if (p.gelu_fp32 & 4) {     // measurement only (VSN_GELU_FP32 bit 2): no aux read, wrong results
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w[j] = 0x3C003C00u + row;
+      } else if (m.wide()) {
         ld_global_v8(ap, w);
         ld_global_v8(ap + 16, w + 8);
       } else {
@@ -192,7 +213,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& pa, int row, int 
           w[4 * j] = u.x; w[4 * j + 1] = u.y; w[4 * j + 2] = u.z; w[4 * j + 3] = u.w;
         }
       }
-      if (p.gelu_fp32 & 2) {
+      if (p.gelu_fp32 & 8) {            // measurement only (bit 3): aux read but no GELU' arithmetic, wrong results
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          f[2 * t] *= bf16lo(w[t]);
+          f[2 * t + 1] *= bf16hi(w[t]);
+        }
+      } else if (p.gelu_fp32 & 2) {
 #pragma unroll
         for (int t = 0; t < 16; ++t) {
           f[2 * t] *= gelu_erf_grad<false>(bf16lo(w[t]));
@@ -292,18 +319,24 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& pa, int row, int 
 template <int BN, int EW, int MODE, bool TWO>
 __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                   const __grid_constant__ CUtensorMap tmB,
+                                                                  const __grid_constant__ CUtensorMap tmAux,
                                                                   const GemmArgs p) {
-  using C = Cfg<BN, TWO>;
+  constexpr bool AUXS = MODE == 5;                 // the epilogue's aux tile is staged in shared memory by TMA
+  static_assert(!AUXS || !TWO, "staged aux tiles are built for single-CTA tiles");
+  using C = Cfg<BN, TWO, AUXS ? 2 : 0>;
   constexpr int EPI_THREADS = EW * 32;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint8_t* aux_s = smem + C::STAGES * C::STAGE_BYTES;                                   // [2][BN/64][128][64] bf16
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::MISC);
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* acc_full = empty_bar + C::STAGES;     // [2] MMA commit -> epilogue
   uint64_t* acc_empty = acc_full + 2;             // [2] epilogue threads -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* bias_s = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);   // [2][256]
-  uint8_t* ones_s = smem + C::STAGES * C::STAGE_BYTES + 256 + 2048;                     // [16][64] bf16, all 1.0
+  uint64_t* aux_full = acc_empty + 2;             // [2] TMA -> epilogue
+  uint64_t* aux_empty = aux_full + 2;             // [2] epilogue threads -> TMA producer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_empty + 2);
+  float* bias_s = reinterpret_cast<float*>(smem + C::MISC + 256);   // [2][256]
+  uint8_t* ones_s = smem + C::MISC + 256 + 2048;                     // [16][64] bf16, all 1.0
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -322,10 +355,13 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
     for (int b = 0; b < 2; ++b) {
       tc::mbar_init(&acc_full[b], 1);
       tc::mbar_init(&acc_empty[b], TWO ? 2 * EPI_THREADS : EPI_THREADS);
+      tc::mbar_init(&aux_full[b], 1);
+      tc::mbar_init(&aux_empty[b], EPI_THREADS);
     }
     tc::fence_barrier_init();
     tc::prefetch_tmap(&tmA);
     tc::prefetch_tmap(&tmB);
+    if constexpr (AUXS) tc::prefetch_tmap(&tmAux);
   }
   if (warp == 1) {
     if constexpr (TWO) tc::tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
@@ -360,7 +396,17 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
       TileCoord t;
       TileIter<TWO> tiles(p, tiles_n, BN, rank);
       int issued = 0;
-      while (tiles.next(t)) {
+      for (int lt = 0; tiles.next(t); ++lt) {
+        if constexpr (AUXS) {
+          // the tile's saved pre-activation, as BN/64 swizzled [128][64] boxes, into the buffer the epilogue of two
+          // tiles ago has finished reading
+          const int ab = lt & 1;
+          tc::mbar_wait(&aux_empty[ab], ((lt >> 1) & 1) ^ 1);
+          tc::mbar_arrive_expect_tx(&aux_full[ab], C::AUX_TILE_BYTES);
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tc::tma_load_2d(aux_s + ab * C::AUX_TILE_BYTES + j * 16384, &tmAux, &aux_full[ab], t.n0 + j * 64, t.m0);
+        }
         for (int i = 0; i < t.nkb; ++i, ++issued, s = (s + 1 == ring ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
           tc::mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * C::STAGE_BYTES;
@@ -487,8 +533,10 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
         tc::named_bar_sync(1, EPI_THREADS);
       }
       tc::mbar_wait(&acc_full[buf], (lt >> 1) & 1);
+      if constexpr (AUXS) tc::mbar_wait(&aux_full[buf], (lt >> 1) & 1);
       tc::fence_after_sync();
       const bool row_ok = row < p.M;
+      const uint8_t* aux_rowp = aux_s + buf * C::AUX_TILE_BYTES + (lg * 32 + lane) * 128;   // + sub-tile * 16384
       float rs = p.alpha;
       if (p.row_scale != nullptr && row_ok) rs *= p.row_scale[row / p.rows_per_group];
       const uint32_t tb = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + buf * BN;
@@ -504,7 +552,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
             tc::tmem_ld_wait();
             if (c0 + NPAR * 32 < BN) tc::tmem_ld_32x32b_x32(tb + c0 + NPAR * 32, v[(i + 1) & 1]);
             const int n = t.n0 + c0;
-            if (row_ok && n < p.N) epilogue_chunk<MODE>(p, row, n, rs, v[i & 1], bs + c0);
+            if (row_ok && n < p.N) epilogue_chunk<(MODE == 5 ? 2 : MODE)>(p, row, n, rs, v[i & 1], bs + c0);   // (MODE 5 runs EW = 16)
           }
         }
       } else {
@@ -514,9 +562,13 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tc_kernel(const __grid_c
           tc::tmem_ld_32x32b_x32(tb + c0, v);
           tc::tmem_ld_wait();
           const int n = t.n0 + c0;
-          if (row_ok && n < p.N) epilogue_chunk<MODE>(p, row, n, rs, v, bs + c0);
+          if (row_ok && n < p.N) {
+            if constexpr (AUXS) epilogue_chunk<MODE>(p, row, n, rs, v, bs + c0, aux_rowp + (c0 >> 6) * 16384, (c0 & 63) >> 3);
+            else epilogue_chunk<MODE>(p, row, n, rs, v, bs + c0);
+          }
         }
       }
+      if constexpr (AUXS) tc::mbar_arrive(&aux_empty[buf]);      // this thread has read its part of the aux tile
       if (p.rowsum != nullptr && t.n0 == 0 && par == 0 && C::RS_COL + 32 <= C::TMEM_COLS) {
         const uint32_t rsv = tc::tmem_ld_32x32b_x1(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + C::RS_COL + buf * 16);
         tc::tmem_ld_wait();
@@ -573,17 +625,20 @@ int make_tmap_2d(CUtensorMap* map, const void* base, long long dim0, long long d
 }
 
 template <int BN, int EW, int MODE, bool TWO>
-int launch_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, int grid, cudaStream_t stream) {
+int launch_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, int grid, cudaStream_t stream,
+                const CUtensorMap* tmAuxp = nullptr) {
+  using CfgT = Cfg<BN, TWO, MODE == 5 ? 2 : 0>;
+  const CUtensorMap& tmAux = tmAuxp != nullptr ? *tmAuxp : tmA;      // unused unless MODE == 5
   static bool attr_set = false;
   if (!attr_set) {
     VSN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EW, MODE, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg<BN, TWO>::SMEM_BYTES));
+                                  CfgT::SMEM_BYTES));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((TWO ? 2 : 1) * grid);
   cfg.blockDim = dim3(64 + EW * 32);
-  cfg.dynamicSmemBytes = Cfg<BN, TWO>::SMEM_BYTES;
+  cfg.dynamicSmemBytes = CfgT::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   int na = 0;
@@ -599,7 +654,7 @@ int launch_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& 
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  VSN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EW, MODE, TWO>, tmA, tmB, a));
+  VSN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EW, MODE, TWO>, tmA, tmB, tmAux, a));
   VSN_LAUNCH_CHECK();
   return 0;
 }
@@ -644,6 +699,17 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs a, int split
         case 3: return launch_mode<BN, EW, 3, true>(tmA, tmB, a, grid, stream);
         case 4: return launch_mode<BN, EW, 4, true>(tmA, tmB, a, grid, stream);
         default: return launch_mode<BN, EW, 0, true>(tmA, tmB, a, grid, stream);
+      }
+    }
+    if constexpr (BN % 64 == 0 && BN <= 192) {
+      // GELU' epilogue with the saved pre-activation staged by TMA: short reductions only (the aux tiles take half of the
+      // operand ring's shared memory); VSN_GEMM_AUX_TMA=0 keeps the global loads (measurements)
+      static int aux_tma = -1;
+      if (aux_tma < 0) { const char* e = getenv("VSN_GEMM_AUX_TMA"); aux_tma = (e != nullptr && e[0] == '0') ? 0 : 1; }
+      if (mode == 2 && aux_tma && ceil_div(a.K, BK) <= Cfg<BN, false, 2>::STAGES && a.ldaux % 8 == 0) {
+        CUtensorMap tmAux;
+        if (int rc = make_tmap_2d(&tmAux, a.aux, a.N, a.M, a.ldaux, 64, BM)) return rc;
+        return launch_mode<BN, EW, 5, false>(tmA, tmB, a, grid, stream, &tmAux);
       }
     }
     switch (mode) {
@@ -768,7 +834,7 @@ extern "C" int vsn_gemm_bf16(const void* A, long long lda, int a_mn, const void*
   a.rowsum = rowsum_out;
   {
     static int gm = -1;
-    if (gm < 0) { const char* e = getenv("VSN_GELU_FP32"); gm = e ? atoi(e) & 3 : 1; }   // default: fp32 forward, packed backward
+    if (gm < 0) { const char* e = getenv("VSN_GELU_FP32"); gm = e ? atoi(e) & 15 : 1; }   // default: fp32 forward, packed backward
     a.gelu_fp32 = gm;
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
