@@ -456,6 +456,7 @@ def summarise_profile(prof, step_ms, peaks):
         ach = top["bytes"] / (top["ms"] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s",
                     "frac": round(ach / hbm_peak, 4), "traffic": None}
+    roofline["algorithmic_bytes_per_step"] = int(top["bytes"])
     roofline.update({"kernel": top_name, "what": "kernel family with the largest share of the step: algorithmic "
                      "flops (bytes) of all its launches / their summed CUDA-event time",
                      "launches_per_step": top["launches"], "ms_per_step": round(top["ms"], 3),
@@ -819,10 +820,13 @@ def native_main(args):
             try:
                 with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
                     tr = json.load(f)
-                ent = tr.get(roofline["kernel"])
-                if ent:
-                    roofline["traffic"] = ent["dram_bytes_per_launch"]
-                    roofline["traffic_of"] = ent["kernel"]
+                # the headline is a kernel FAMILY over one step, so its traffic is the family's DRAM bytes per step
+                # (scripts/family_traffic.py over an ncu launch list with the dram__bytes metrics), beside the
+                # algorithmic bytes per step `achieved` is computed from
+                ent = tr.get("family:" + roofline["kernel"])
+                if ent and args.model == "swin" and not args.sam and not args.no_fuse_micro:
+                    roofline["traffic"] = ent["dram_bytes_per_step"]
+                    roofline["traffic_unit"] = "DRAM bytes per step, all launches of the family"
                     roofline["traffic_source"] = ent["source"]
             except OSError:
                 pass

@@ -39,9 +39,10 @@ def main():
         dyc = r(M, K).to(BF)
         cases.append((f"dgrad+gelu' M{M} N{N} K{K}", lambda dyc=dyc, w2=w2, h=h: ops.linear_dgrad(dyc, w2, gelu_aux=h), 2 * M * N * K,
                       2 * M * K + 4 * M * N))
-    for (M, N, K) in [(435456, 288, 96), (435456, 96, 384), (16128, 384, 1536), (16128, 1152, 384)]:
+    for (M, N, K) in [(435456, 288, 96), (435456, 96, 384), (435456, 96, 96), (54432, 192, 768), (54432, 192, 192),
+                      (16128, 384, 1536), (16128, 384, 384), (16128, 1152, 384), (2016, 768, 3072)]:
         x, w, b = r(M, K).to(BF), (0.05 * r(N, K)).to(BF), r(N)
-        res = r(M, N) if N in (96, 384) else None
+        res = r(M, N) if N in (96, 192, 384, 768) else None
         cases.append((f"fwd {'resid f32' if res is not None else 'bf16'} M{M} N{N} K{K}",
                       lambda x=x, w=w, b=b, res=res: ops.linear_fwd(x, w, b, out_dtype=F32 if res is not None else BF, resid=res),
                       2 * M * N * K, 2 * M * K + (8 if res is not None else 2) * M * N))
