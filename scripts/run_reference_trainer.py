@@ -18,6 +18,12 @@ What it sets up, all outside the reference's files:
 Then `runpy` executes the trainer as `__main__`.  With `--resume` the run is repeated from the `_last.pt` checkpoint
 the first run wrote; `--compare` loads that checkpoint into the reference's own model class on the CPU and compares
 its logits with the drop-in model's on the same input.
+
+`--eval` drives the UNMODIFIED evaluation script (eval/eval_transformer.py: build_model from the run's saved W&B config,
+load_checkpoint, channels_last_3d inputs under torch.inference_mode, optional fp16 autocast, bootstrap metrics, the
+prediction CSVs) over the checkpoints the trainer wrote, the drop-in modules shadowing the reference's;
+`--eval --reference-models` is the control run (the reference's own modules, any device), and `--eval-compare` checks
+the two runs' prediction CSVs against each other (same checkpoints, same subjects: class probabilities).
 """
 from __future__ import annotations
 
@@ -177,6 +183,67 @@ def compare_checkpoint(out, arch, img):
     assert err < 2e-2, err
 
 
+def run_eval(a, out, ref_root):
+    """eval/eval_transformer.py as __main__ over every checkpoint of the harness run (its own argv, its own W&B config
+    lookup next to the checkpoints: train/train_transformer.py passes dir=save_dir to wandb.init)."""
+    import glob
+    save_dir = os.path.join(out, "runs", f"{a.arch}_harness")
+    cks = sorted(glob.glob(os.path.join(save_dir, "model_*_last.pt")) + glob.glob(os.path.join(save_dir, "model_*_best*.pt")))
+    if a.eval_last_only:
+        cks = [c for c in cks if c.endswith("_last.pt")]
+    if not cks:
+        raise SystemExit("eval: the trainer harness has written no checkpoint under " + save_dir)
+    if not a.reference_models:
+        sys.path.insert(0, os.path.join(ROOT, "vit-stability-neurodegeneration_b200", "dropin"))
+    sys.path.append(ref_root)
+    folder = a.eval_folder or ("eval_reference" if a.reference_models else "eval_dropin")
+    argv = ["eval_transformer.py", "--training-csv-dir", os.path.join(out, "folds"), "--intermediate-dir",
+            os.path.join(out, "cache"), "--checkpoints", *cks, "--batch-size", "2", "--force-eval", "--output-folder", folder]
+    if a.use_amp:
+        argv.append("--use-amp")
+    os.chdir(ref_root)
+    os.environ.setdefault("WANDB_SILENT", "true")
+    # utils/bootstrap_metric.py:594-598 picks joblib's threading backend on its cluster (SLURM_JOB_ID set) and loky
+    # elsewhere; loky's worker processes cannot import the harness's monai / timm stand-ins, so the harness takes the
+    # reference's own cluster branch
+    os.environ.setdefault("SLURM_JOB_ID", "harness")
+    # ... and the metric post-processing (10000 bootstrap resamples per split, minutes under the GIL) is cut to 200: the
+    # script's `from utils import compute_bootstrap_metrics` binds this wrapper; nothing on the model path changes
+    import functools
+    import utils as ref_utils
+    ref_utils.compute_bootstrap_metrics = functools.partial(ref_utils.compute_bootstrap_metrics, n_bootstrap=a.bootstrap)
+    sys.argv = argv
+    print(f"harness: eval_transformer.py over {len(cks)} checkpoints -> {os.path.join(save_dir, folder)}", flush=True)
+    runpy.run_path(os.path.join(ref_root, "eval", "eval_transformer.py"), run_name="__main__")
+
+
+def compare_eval(out, arch, tol):
+    """The prediction CSVs eval_transformer.py wrote through the drop-in against the control run's (reference modules)."""
+    import glob
+    import numpy as np
+    import pandas as pd
+    save_dir = os.path.join(out, "runs", f"{arch}_harness")
+    ours = sorted(glob.glob(os.path.join(save_dir, "eval_dropin", "prediction_*_id.csv")))
+    if not ours:
+        raise SystemExit("eval-compare: no drop-in predictions")
+    worst = 0.0
+    for p in ours:
+        q = os.path.join(save_dir, "eval_reference", os.path.basename(p))
+        if not os.path.exists(q):
+            raise SystemExit("eval-compare: no control prediction file " + q)
+        da, db = pd.read_csv(p), pd.read_csv(q)
+        assert list(da["Subject"]) == list(db["Subject"]), "subjects differ"
+        cols = [c for c in da.columns if c not in db.columns or da[c].dtype.kind == "f"]
+        cols = [c for c in cols if c in db.columns and db[c].dtype.kind == "f" and c not in ("Age",)]
+        pa, pb = da[cols].to_numpy(dtype=np.float64), db[cols].to_numpy(dtype=np.float64)
+        err = float(np.abs(pa - pb).max())
+        worst = max(worst, err)
+        print(f"eval-compare: {os.path.basename(p)}: {len(da)} subjects, columns {cols}, max |dp| {err:.3e}; "
+              f"same argmax {int((pa.argmax(1) == pb.argmax(1)).sum())}/{len(da)}")
+    assert worst < tol, (worst, tol)
+    print(f"eval-compare: ok (worst {worst:.3e} < {tol})")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--arch", default="swin", choices=["swin", "vit"])
@@ -186,6 +253,13 @@ def main():
     ap.add_argument("--resume", action="store_true", help="resume from the _last.pt checkpoint of a previous run")
     ap.add_argument("--compare", action="store_true",
                     help="no training: load the run's _last.pt into the reference model (CPU) and the drop-in (GPU)")
+    ap.add_argument("--eval", action="store_true", help="run the unmodified eval/eval_transformer.py over the run's checkpoints")
+    ap.add_argument("--eval-compare", action="store_true", help="compare the drop-in and the control prediction CSVs")
+    ap.add_argument("--eval-last-only", action="store_true", help="eval: only the *_last.pt checkpoint")
+    ap.add_argument("--eval-folder", default=None)
+    ap.add_argument("--bootstrap", type=int, default=200, help="eval: bootstrap resamples of the metric post-processing")
+    ap.add_argument("--eval-tol", type=float, default=2e-2, help="largest allowed |difference| of a class probability")
+    ap.add_argument("--use-amp", action="store_true", help="eval: pass --use-amp (fp16 autocast around the model call)")
     ap.add_argument("--reference-models", action="store_true",
                     help="do NOT shadow the reference's modules (control run of the harness itself, any device)")
     a = ap.parse_args()
@@ -195,7 +269,11 @@ def main():
     img = tuple(a.img_size) if a.img_size else ((48, 56, 48) if a.arch == "swin" else (48, 64, 48))
     if a.compare:
         return compare_checkpoint(out, a.arch, img)
+    if a.eval_compare:
+        return compare_eval(out, a.arch, a.eval_tol)
     ref_root = install_stubs()
+    if a.eval:
+        return run_eval(a, out, ref_root)
     rank = int(os.environ.get("RANK", "0"))
     if rank == 0:
         csv_dir, cache, n = make_cohort(out, img, classes)

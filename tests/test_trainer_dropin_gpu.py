@@ -1,7 +1,9 @@
 """The UNMODIFIED reference trainer (train/train_transformer.py from baseline/_ref) driven through vsn_b200's drop-in
 packages on a synthetic cohort: SAM(AdamW) + EMA + MixUp + balanced sampler, fp16 autocast + GradScaler, validation
 with ema.apply_to / restore, asynchronous checkpoints; then the checkpoint it wrote is loaded strictly into the
-reference's own model class (CPU fp32) and into the drop-in (GPU) and the logits are compared (2e-2, bf16 path).
+reference's own model class (CPU fp32) and into the drop-in (GPU) and the logits are compared (2e-2, bf16 path);
+then the UNMODIFIED evaluation script (eval/eval_transformer.py) runs over those checkpoints through the drop-in and its
+prediction CSVs are compared with a control run on the reference's own modules.
 Needs baseline/_ref (scripts/install_ref.sh; it travels with the gpurun snapshot): skipped where it is absent."""
 import os
 import subprocess
@@ -34,6 +36,19 @@ def test_unmodified_trainer_runs_on_the_dropin_and_checkpoints_interchange(arch,
     assert "Step 6" in log
     log = _run("--arch", arch, "--out", out, "--compare")
     assert "loaded strictly into the reference" in log
+    # the UNMODIFIED evaluation script (eval/eval_transformer.py) over the checkpoints that run wrote: through the drop-in
+    # (fp32 call and fp16-autocast call), then the control run with the reference's own modules, then the prediction
+    # CSVs of the two against each other (class probabilities, bf16 path: 2e-2 absolute)
+    fast = ("--eval-last-only", "--bootstrap", "20")
+    log = _run("--arch", arch, "--out", out, "--eval", *fast)
+    assert "Saved in-domain predictions" in log and "Test (ID)" in log
+    if arch == "swin":
+        log = _run("--arch", arch, "--out", out, "--eval", "--use-amp", "--eval-folder", "eval_dropin_amp", *fast)
+        assert "Saved in-domain predictions" in log
+    log = _run("--arch", arch, "--out", out, "--eval", "--reference-models", *fast)
+    assert "Saved in-domain predictions" in log
+    log = _run("--arch", arch, "--out", out, "--eval-compare")
+    assert "eval-compare: ok" in log
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="baseline/_ref not installed")
