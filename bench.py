@@ -404,7 +404,9 @@ def reference_main(args):
 
 # ------------------------------------------------------------------------------------------- roofline tables
 FAMILIES = {"vsn_gemm_bf16": "gemm", "vsn_attn_fwd": "attention_fwd", "vsn_attn_bwd": "attention_bwd",
-            "vsn_layernorm_fwd": "layernorm", "vsn_layernorm_bwd": "layernorm", "vsn_colreduce": "layernorm"}
+            "vsn_layernorm_fwd": "layernorm", "vsn_layernorm_bwd": "layernorm", "vsn_colreduce": "layernorm",
+            "vsn_merge_ln_fwd": "layernorm", "vsn_merge_ln_bwd": "layernorm", "vsn_patch_ln_fwd": "layernorm",
+            "vsn_patch_ln_param_grad": "layernorm"}
 
 
 def summarise_profile(prof, step_ms, peaks):
