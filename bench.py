@@ -298,44 +298,72 @@ def swin_state_shapes(classes):
 
 
 
-def tta_ensemble_arm(args, dev, subjects=2, snapshots=10, steps=3, warmup=1):
+def tta_ensemble_arm(args, dev, subjects=2, snapshots=10, steps=3, warmup=1, be=None):
     """BASELINE config 5: Swin-3D (swin-5c) evaluation with test-time augmentation (8 views: identity, flip, 5 affine,
     centre crop + resize) and a 10-snapshot ensemble (eval/test_time_augmentation.py:221-354,
-    scripts/transformer.sh:241-266).  A step = `subjects` normalised fp16 volumes copied from pinned host memory, all
-    views written by one kernel, one [subjects*8] forward per snapshot (weights swapped in with load_state_dict), the
-    entropy-weighted averages and the D2H read of the probabilities.  volumes/s = subjects / step time."""
+    scripts/transformer.sh:241-266).  A step = `subjects` normalised fp16 volumes PER GPU copied from pinned host
+    memory, all views written by one kernel, one [subjects*8] forward per snapshot (weights swapped in with
+    load_state_dict), the entropy-weighted averages and the D2H read of the probabilities.  On N > 1 GPUs
+    (`be.world`; every rank calls this) the subject list of a step is N * subjects long, every rank predicts its
+    contiguous shard (vsn_b200.tta.ShardedInference) and one all-gather hands every rank the full [N*subjects, K]
+    table: no collective in the data path, `scaling: weak`.  volumes/s = all subjects of a step / step time (max over
+    ranks)."""
     import torch
     import vsn_b200  # noqa: F401
     from vsn_b200.swin_model import SwinTransformerT
-    from vsn_b200.tta import TestTimeAugmentation, SnapshotEnsemble
-    torch.manual_seed(0)
-    model = SwinTransformerT(in_channels=1, mlp_ratio=4.0, qkv_bias=True, dropout=0.0, attention_dropout=0.0,
-                             stochastic_depth_prob=0.15, num_classes=5, norm_layer=torch.nn.LayerNorm, **SWIN).to(dev).eval()
-    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
-    snaps = [sd0] + [{k: (v + 1e-3 * torch.randn_like(v) if v.is_floating_point() else v.clone()) for k, v in sd0.items()}
-                     for _ in range(snapshots - 1)]
-    tta = TestTimeAugmentation(model, dev, num_samples=5, seed=0)
-    ens = SnapshotEnsemble(model, snaps, tta)
-    vol = VOLUMES["swin"]
-    host = torch.randn(subjects, 1, *vol).half().pin_memory()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    probs = None
-    for i in range(warmup + steps):
-        if i == warmup:
-            torch.cuda.synchronize()
-            e0.record()
-        probs = ens.predict(host).cpu()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
+    from vsn_b200.tta import TestTimeAugmentation, SnapshotEnsemble, ShardedInference
+    world = be.world if be is not None else 1
+    ok, err = 1, ""
+    try:
+        torch.manual_seed(0)
+        model = SwinTransformerT(in_channels=1, mlp_ratio=4.0, qkv_bias=True, dropout=0.0, attention_dropout=0.0,
+                                 stochastic_depth_prob=0.15, num_classes=5, norm_layer=torch.nn.LayerNorm, **SWIN).to(dev).eval()
+        sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+        snaps = [sd0] + [{k: (v + 1e-3 * torch.randn_like(v) if v.is_floating_point() else v.clone()) for k, v in sd0.items()}
+                         for _ in range(snapshots - 1)]
+        tta = TestTimeAugmentation(model, dev, num_samples=5, seed=0)
+        ens = SnapshotEnsemble(model, snaps, tta)
+        vol = VOLUMES["swin"]
+        host = torch.randn(subjects * world, 1, *vol, generator=torch.Generator().manual_seed(77)).half().pin_memory()
+        sharded = ShardedInference(ens, batch=subjects)
+    except RuntimeError as e:                # e.g. out of memory on one rank: every rank must learn of it before a collective
+        ok, err = 0, str(e).splitlines()[0][:200]
+    if world > 1:
+        t = torch.tensor([ok], device=dev)
+        be.dist.all_reduce(t, op=be.dist.ReduceOp.MIN)
+        ok = int(t.item())
+    if not ok:
+        return {"unavailable": err or "another rank failed to set the arm up"}
+    probs = [None]
+
+    def step():
+        probs[0] = sharded.predict(host, device=dev).cpu()
+
+    if be is not None:
+        for _ in range(warmup):
+            step()
+        ms = be.timed(step, steps) / steps
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(warmup + steps):
+            if i == warmup:
+                torch.cuda.synchronize()
+                e0.record()
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    p = probs[0]
     views = tta.get_num_augmentations()
-    return {"value": round(subjects / (ms * 1e-3), 2), "unit": "volumes/s", "ms_per_step": round(ms, 3),
+    n = subjects * world
+    return {"value": round(n / (ms * 1e-3), 2), "unit": "volumes/s", "ms_per_step": round(ms, 3),
             "config": {"workload": "Swin-3D (Swin-T, swin-5c) inference, test-time augmentation + snapshot ensemble",
-                       "volume": list(vol), "subjects_per_step": subjects, "views": views, "snapshots": snapshots,
-                       "forward_volumes_per_step": subjects * views * snapshots},
-            "forward_volumes_per_s": round(subjects * views * snapshots / (ms * 1e-3), 1),
-            "h2d_bytes_per_step": int(host.numel() * 2), "d2h_bytes_per_step": int(probs.numel() * 4),
-            "probabilities_sum_to_one": bool(float((probs.sum(-1) - 1).abs().max()) < 1e-4)}
+                       "volume": list(vol), "subjects_per_step": n, "subjects_per_gpu": subjects, "n_gpus": world,
+                       "views": views, "snapshots": snapshots, "forward_volumes_per_step": n * views * snapshots,
+                       "parallelism": f"subjects sharded over {world} GPU(s), one all-gather of [{n}, 5] per step" if world > 1 else "1 GPU"},
+            "forward_volumes_per_s": round(n * views * snapshots / (ms * 1e-3), 1),
+            "h2d_bytes_per_step": int(host.numel() * 2 // world), "d2h_bytes_per_step": int(p.numel() * 4),
+            "probabilities_sum_to_one": bool(p.shape[0] == n and float((p.sum(-1) - 1).abs().max()) < 1e-4)}
 
 
 def eager_cuda_arm(args, steps=3, warmup=2):
@@ -884,6 +912,13 @@ def native_main(args):
                 "ms_per_step": round(m3["ms"] / max(2, args.steps // 2), 3),
                 "e2e": {"value": round(m3["e2e"], 2), "unit": "volumes/s"}}
             del w3
+            gc.collect()
+            be.torch.cuda.empty_cache()
+            be.sync_all()
+
+        if world > 1:
+            # BASELINE config 5 on N GPUs: every rank predicts its shard of the step's subjects, one all-gather at the end
+            extras["swin5c_tta_ensemble_infer"] = tta_ensemble_arm(args, be.dev, be=be)
             gc.collect()
             be.torch.cuda.empty_cache()
             be.sync_all()

@@ -181,3 +181,65 @@ class SnapshotEnsemble:
         return total / len(self.snapshots)
 
     __call__ = predict
+
+
+def shard_range(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous shard [lo, hi) of n subjects for `rank`: sizes differ by at most one, the first n % world ranks take
+    the longer ones (a rank may get nothing when n < world)."""
+    base, extra = divmod(int(n), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+class ShardedInference:
+    """BASELINE config 5 on several GPUs: inference is embarrassingly parallel over subjects, so every
+    rank predicts one contiguous shard of the subject list with its own predictor (a `TestTimeAugmentation`, a
+    `SnapshotEnsemble` or the bare model wrapped in softmax -- all views and snapshots of a subject stay on the rank
+    that owns it) and ONE all-gather of the `[n, K]` probabilities at the end gives every rank the full table in subject
+    order.  No collective inside the data path.  The reference evaluates checkpoints one process at a time
+    (eval/eval_transformer.py:1052-1157, scripts/transformer.sh:241-266); this is the batch-sharded form of that loop.
+
+    `predictor(x[b,1,D,H,W]) -> [b, K]` probabilities; `group=None` is the default process group; without an
+    initialised process group the class degrades to the plain loop (world 1)."""
+
+    def __init__(self, predictor, group=None, batch: int = 2):
+        import torch.distributed as dist
+        self.predictor, self.group, self.batch = predictor, group, max(1, int(batch))
+        self._dist = dist if (dist.is_available() and dist.is_initialized()) else None
+        self.world = self._dist.get_world_size(group) if self._dist else 1
+        self.rank = self._dist.get_rank(group) if self._dist else 0
+
+    @torch.no_grad()
+    def predict_local(self, volumes: torch.Tensor) -> Tuple[torch.Tensor, Tuple[int, int]]:
+        """This rank's shard of `volumes` [N,1,D,H,W] (host or device): ([hi - lo, K] probabilities, (lo, hi))."""
+        lo, hi = shard_range(volumes.shape[0], self.world, self.rank)
+        outs = [self.predictor(volumes[i:min(i + self.batch, hi)]).float() for i in range(lo, hi, self.batch)]
+        return (torch.cat(outs) if outs else torch.zeros(0, 0)), (lo, hi)
+
+    @torch.no_grad()
+    def gather(self, local: torch.Tensor, n: int, device=None) -> torch.Tensor:
+        """All ranks call this once: `[n, K]` in subject order on every rank (ranks without subjects join with zero rows)."""
+        if self.world == 1:
+            return local
+        dist = self._dist
+        dev = local.device if local.numel() else (torch.device(device) if device is not None else local.device)
+        k = torch.tensor([local.shape[1] if local.ndim == 2 else 0], device=dev, dtype=torch.int64)
+        dist.all_reduce(k, op=dist.ReduceOp.MAX, group=self.group)          # empty shards do not know K
+        K = int(k.item())
+        cap = -(-n // self.world)                                            # longest shard
+        pad = torch.zeros(cap, K, device=dev, dtype=torch.float32)
+        if local.numel():
+            pad[:local.shape[0]] = local.to(dev)
+        parts = [torch.empty_like(pad) for _ in range(self.world)]
+        dist.all_gather(parts, pad, group=self.group)
+        rows = []
+        for r, part in enumerate(parts):
+            lo, hi = shard_range(n, self.world, r)
+            rows.append(part[:hi - lo])
+        return torch.cat(rows)
+
+    def predict(self, volumes: torch.Tensor, device=None) -> torch.Tensor:
+        local, _ = self.predict_local(volumes)
+        return self.gather(local, volumes.shape[0], device=device)
+
+    __call__ = predict
