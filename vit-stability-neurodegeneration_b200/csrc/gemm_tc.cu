@@ -760,6 +760,23 @@ extern "C" int vsn_gemm_bf16(const void* A, long long lda, int a_mn, const void*
   else if (N <= 96) BN = 96;
   else BN = 128;
   if (rowsum_out != nullptr && BN == 256) BN = 128;   // the row-sum accumulators need 32 spare TMEM columns
+  // Tile-width fallback: smaller tiles while the problem has fewer tiles than the chip has SMs.  Atomic outputs (the
+  // wgrad GEMMs) run whole waves of the persistent grid, and 85 % of a wave is a wave: 144 tiles of 128 x 192 on 148 SMs
+  // must not fall back to three times as many 64-wide ones (measured at 32256 tokens, N 1536, K 384: 93 us after the
+  // fallback against 50 us for the best split without it).  VSN_WGRAD_WANT_PCT / VSN_WGRAD_MODEL=0: measurements only.
+  static int want_pct = -1, wgrad_model = -1;
+  if (want_pct < 0) { const char* e = getenv("VSN_WGRAD_WANT_PCT"); want_pct = e ? atoi(e) : 85; }
+  if (wgrad_model < 0) { const char* e = getenv("VSN_WGRAD_MODEL"); wgrad_model = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  const int want_tiles = out_kind == 2 ? (vsn_num_sms() * want_pct) / 100 : vsn_num_sms();
+  auto narrowed = [&](int bn, int sk) {
+    while (bn > 64 && ceil_div(M, BM) * ceil_div(N, bn) * sk < want_tiles) {
+      const int next = bn == 256 ? 128 : bn == 192 ? (b_mn ? 64 : 96) : bn == 128 ? 64 : bn == 96 ? (N % 64 == 0 || N <= 64 ? 64 : 96) : 64;
+      if (next == bn) break;
+      if (N % next != 0 && next < N) break;   // keep tiles exact when they were exact
+      bn = next;
+    }
+    return bn;
+  };
   if (split_k == 0 && out_kind == 2) {
     // Automatic split of the reduction for atomic outputs (the wgrad GEMMs: few output tiles, a very long K).
     const int base = ceil_div(M, BM) * ceil_div(N, BN), nkb_all = ceil_div(K, BK), sms = vsn_num_sms();
@@ -775,24 +792,33 @@ extern "C" int vsn_gemm_bf16(const void* A, long long lda, int a_mn, const void*
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
       }
       split_k = best;
+    } else if (wgrad_model) {
+      // Many output tiles (late stages, operands resident in L2): the kernel is bound by the operand bytes its CTAs pull
+      // per k-block, (128 + BN) x 64 x 2, and runs in rounds of one tile per SM.  Cost of a split = rounds x (k-blocks
+      // per tile x (128 + BN) + the tile's epilogue, ~6 x BN in the same unit), BN being the width the fallback above
+      // leaves for that split.  The model reproduces the measured sweep (scripts/exp_wgrad_split.py: 1.6-1.9 ns per unit
+      // over splits 4..48 at 32256 tokens) and replaces "two 128 x 128 tiles per SM", which left a 30 %-filled second
+      // round at N 1536 / 1152, K 384 (67.6 -> 50.5 us, 55.4 -> 41.2 us at the best fixed split).
+      long long best_cost = -1;
+      int best = 1;
+      const int tm = ceil_div(M, BM);
+      for (int s = 1; s <= nkb_all && s <= 64; ++s) {
+        const int kb = ceil_div(nkb_all, s), se = ceil_div(nkb_all, kb);
+        if (se != s) continue;                           // the same effective split as a smaller s
+        const int bn = narrowed(BN, se);
+        const long long tiles = static_cast<long long>(tm) * ceil_div(N, bn) * se;
+        const long long cost = ceil_div_ll(tiles, sms) * (static_cast<long long>(kb) * (128 + bn) + 6LL * bn);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
+      }
+      split_k = best;
     } else {
-      // Many output tiles (late stages, operands resident in L2): about two 128 x 128 tiles' worth of work per SM
-      // measured best (more, shorter tiles than a single full wave).
+      // (the rule the model replaced: about two 128 x 128 tiles' worth of work per SM)
       const int t128 = ceil_div(M, 128) * ceil_div(N, N <= 64 ? 64 : 128);
       int s = (2 * sms) / (t128 > 0 ? t128 : 1);
       split_k = s < 1 ? 1 : (s > nkb_all ? nkb_all : s);
     }
   }
-  {
-    const int want = vsn_num_sms();
-    const int sk = split_k < 1 ? 1 : split_k;
-    while (BN > 64 && ceil_div(M, BM) * ceil_div(N, BN) * sk < want) {
-      const int next = BN == 256 ? 128 : BN == 192 ? (b_mn ? 64 : 96) : BN == 128 ? 64 : BN == 96 ? (N % 64 == 0 || N <= 64 ? 64 : 96) : 64;
-      if (next == BN) break;
-      if (N % next != 0 && next < N) break;   // keep tiles exact when they were exact
-      BN = next;
-    }
-  }
+  BN = narrowed(BN, split_k < 1 ? 1 : split_k);
   // CTA pairs (cta_group::2, 256 x BN tiles): for store epilogues with at least two m-tiles; an MN-major B operand is
   // loaded in 64-column boxes, so its half tile must be a whole number of them.
   bool pair;
