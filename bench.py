@@ -61,8 +61,11 @@ def parse(argv=None):
     ap.add_argument("--no-fuse-micro", action="store_true",
                     help="accumulate the micro-batches one forward/backward at a time, as the reference's loop does, "
                          "instead of one pass over their concatenation (same gradients)")
-    ap.add_argument("--no-graph-comm", action="store_true",
-                    help="N>1, graph mode: reduce the buckets after the last replay instead of inside the graph")
+    ap.add_argument("--graph-comm", action="store_true",
+                    help="N>1, graph mode: capture the bucket all-reduces INSIDE the last micro-batch's graph (overlapped "
+                         "with backward) instead of reducing after the last replay.  Measured slower on 2 B200 (1672 vs "
+                         "1704 volumes/s): the NCCL kernels take SMs from the persistent one-CTA-per-SM grids they overlap")
+    ap.add_argument("--no-graph-comm", action="store_true", help="(the default since round 2; kept for old command lines)")
     ap.add_argument("--torch-ddp", action="store_true", help="N>1: use torch DDP instead of vsn_b200.ddp.GradAllReduce")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the instrumented pass (roofline = null)")
@@ -560,7 +563,7 @@ class CudaBackend:
         if self._lib.PRECISION == "f16":      # half-precision gradients need the reference's loss scaling (:1141-1160)
             scaler = torch.amp.GradScaler("cuda", init_scale=1024.0, growth_interval=100)
         ts = TrainStep(model, use_sam=args.sam, use_ema=not args.no_ema, ddp_model=ddp, grad_sync=sync, graph=graph,
-                       graph_comm=not args.no_graph_comm, fuse_micro_batches=not args.no_fuse_micro, scaler=scaler)
+                       graph_comm=args.graph_comm and not args.no_graph_comm, fuse_micro_batches=not args.no_fuse_micro, scaler=scaler)
         G = args.micro_batches
         vol = VOLUMES[args.model]
         host = [synth_batch(args.batch, args.classes, seed=1234 + self.rank * 100 + i, volume=vol) for i in range(G)]

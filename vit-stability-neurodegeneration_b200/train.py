@@ -66,13 +66,17 @@ class TrainStep:
     graph_comm  (N > 1, graph mode) capture a second graph for the LAST micro-batch of a pass with the bucket
                 all-reduces inside it: NCCL runs on the communication stream as a forked branch of the graph, each
                 bucket as soon as backward has completed it, so the exchange overlaps the rest of backward exactly as
-                in the eager loop.  Off: the buckets are reduced after the last replay (exposed, ~0.5 ms for 117 MB).
+                in the eager loop.  Off (the default): the buckets are reduced after the last replay, exposed.
+                Measured on 2 B200 at the round's final state: exposed 18.78 ms per step (+0.41 ms over one GPU), in-graph
+                19.13 ms (+0.76 ms) -- every kernel of the backward pass is a persistent grid of one CTA per SM, so an
+                NCCL kernel that overlaps them takes SMs away and the grid it displaces waits for it; the "overlap" costs
+                more than the 117 MB take on NVLink by themselves (profiles/r2x_*, r2y_*).
     """
 
     def __init__(self, model: torch.nn.Module, *, lr: float = 1e-4, weight_decay: float = 0.05, use_sam: bool = False,
                  sam_rho: float = 0.05, use_ema: bool = True, ema_decay: float = 0.999, smoothing: float = 0.1,
                  ddp_model: Optional[torch.nn.Module] = None, grad_sync: Optional[GradAllReduce] = None,
-                 graph: bool = False, graph_comm: bool = True, fused_adamw: bool = True, fuse_micro_batches: bool = False,
+                 graph: bool = False, graph_comm: bool = False, fused_adamw: bool = True, fuse_micro_batches: bool = False,
                  scaler: Optional["torch.amp.GradScaler"] = None):
         self.module = model                       # the bare module (EMA / parameters)
         self.model = ddp_model if ddp_model is not None else model   # what forward is called on
