@@ -222,6 +222,8 @@ class ShardedInference:
         if self.world == 1:
             return local
         dist = self._dist
+        if device is None and not local.numel() and dist.get_backend(self.group) == "nccl":
+            device = torch.device("cuda", torch.cuda.current_device())      # a rank without subjects still needs a CUDA buffer
         dev = local.device if local.numel() else (torch.device(device) if device is not None else local.device)
         k = torch.tensor([local.shape[1] if local.ndim == 2 else 0], device=dev, dtype=torch.int64)
         dist.all_reduce(k, op=dist.ReduceOp.MAX, group=self.group)          # empty shards do not know K
